@@ -1,0 +1,230 @@
+"""ctypes front-end of the CPU oracle (oracle/minsnap_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm;
+the product package never imports this module.
+
+Two builds of the same C file are exposed: ``f64`` (double arithmetic: the parity oracle and
+the CPU baseline) and ``ld`` (x87 long double arithmetic: extended-precision ground truth).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBDIR = os.path.join(_HERE, "lib")
+
+
+def build(force=False):
+    """Compile both oracle shared objects with oracle/Makefile (gcc, seconds)."""
+    need = force or not all(
+        os.path.exists(os.path.join(_LIBDIR, n)) for n in ("liboracle_f64.so", "liboracle_ld.so"))
+    src_m = os.path.getmtime(os.path.join(_HERE, "minsnap_oracle.c"))
+    if not need:
+        need = any(os.path.getmtime(os.path.join(_LIBDIR, n)) < src_m
+                   for n in ("liboracle_f64.so", "liboracle_ld.so"))
+    if need:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+
+
+class Oracle:
+    def __init__(self, precision="f64"):
+        build()
+        assert precision in ("f64", "ld")
+        self.lib = C.CDLL(os.path.join(_LIBDIR, "liboracle_%s.so" % precision))
+        self.real = np.float64 if precision == "f64" else np.longdouble
+        self.creal = C.c_double if precision == "f64" else C.c_longdouble
+        assert self.lib.orc_real_bytes() == np.dtype(self.real).itemsize
+        self.lib.orc_polynomial_evaluate.restype = self.creal
+        self.lib.orc_compute_cost.restype = self.creal
+        self.precision = precision
+
+    # -- helpers -------------------------------------------------------------------
+    def _r(self, a):
+        return np.ascontiguousarray(np.asarray(a, dtype=self.real))
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    # -- small matrices ------------------------------------------------------------
+    def base_coefficients(self, n):
+        out = np.zeros((n, n), self.real)
+        self.lib.orc_base_coefficients(n, self._p(out))
+        return out
+
+    def mapping_matrix(self, N, T):
+        A = np.zeros((N, N), self.real)
+        self.lib.orc_setup_mapping_matrix(C.c_int(N), self.creal(T), self._p(A))
+        return A
+
+    def invert_mapping_matrix(self, A):
+        A = self._r(A)
+        N = A.shape[0]
+        Ai = np.zeros((N, N), self.real)
+        st = self.lib.orc_invert_mapping_matrix(N, self._p(A), self._p(Ai))
+        assert st == 0
+        return Ai
+
+    def dense_inverse(self, M):
+        M = self._r(M)
+        n = M.shape[0]
+        Mi = np.zeros((n, n), self.real)
+        assert self.lib.orc_dense_inverse(n, self._p(M), self._p(Mi)) == 0
+        return Mi
+
+    def cost_matrix(self, N, derivative, T):
+        Q = np.zeros((N, N), self.real)
+        self.lib.orc_quadratic_cost_jacobian(C.c_int(N), C.c_int(derivative), self.creal(T), self._p(Q))
+        return Q
+
+    def segment_hessian(self, N, derivative, T):
+        H = np.zeros((N, N), self.real)
+        assert self.lib.orc_segment_hessian(C.c_int(N), C.c_int(derivative), self.creal(T), self._p(H)) == 0
+        return H
+
+    # -- reordering ----------------------------------------------------------------
+    def reorder(self, N, K, mask):
+        mask = np.ascontiguousarray(np.asarray(mask, np.uint8).reshape(K + 1, N // 2))
+        col = np.zeros(N * K, np.int32)
+        nf = C.c_int32()
+        npf = C.c_int32()
+        st = self.lib.orc_constraint_reordering(N, K, self._p(mask), self._p(col), C.byref(nf), C.byref(npf))
+        assert st == 0
+        return col, nf.value, npf.value
+
+    # -- solve ---------------------------------------------------------------------
+    def solve(self, N, K, D, derivative, mask, vertex_values, times, want_R=False):
+        """mask[(K+1)][N/2], vertex_values[(K+1)][N/2][D], times[K].
+        Returns dict(coeffs[K][D][N], d_fixed[D][nf], d_free[D][np], cost, status[, R])."""
+        h = N // 2
+        mask = np.ascontiguousarray(np.asarray(mask, np.uint8).reshape(K + 1, h))
+        vals = self._r(vertex_values).reshape(K + 1, h, D)
+        times = self._r(times).reshape(K)
+        n_fixed = int(mask.sum())
+        n_free = (K + 1) * h - n_fixed
+        coeffs = np.zeros((K, D, N), self.real)
+        d_fixed = np.zeros((D, n_fixed), self.real)
+        d_free = np.zeros((D, n_free), self.real)
+        cost = np.zeros(1, self.real)
+        R = np.zeros((n_fixed + n_free, n_fixed + n_free), self.real) if want_R else None
+        st = self.lib.orc_solve_linear(N, K, D, derivative, self._p(mask), self._p(vals), self._p(times),
+                                       self._p(coeffs), self._p(d_fixed), self._p(d_free), self._p(cost),
+                                       self._p(R) if want_R else None)
+        out = dict(coeffs=coeffs, d_fixed=d_fixed, d_free=d_free, cost=cost[0], status=st)
+        if want_R:
+            out["R"] = R
+        return out
+
+    def coeffs_from_constraints(self, N, K, D, col_of_row, d_all, times):
+        col = np.ascontiguousarray(np.asarray(col_of_row, np.int32))
+        d_all = self._r(d_all)
+        n_all = d_all.shape[1]
+        times = self._r(times)
+        coeffs = np.zeros((K, D, N), self.real)
+        st = self.lib.orc_coeffs_from_constraints(N, K, D, self._p(col), n_all, self._p(d_all),
+                                                  self._p(times), self._p(coeffs))
+        assert st == 0
+        return coeffs
+
+    def compute_cost(self, N, K, D, derivative, coeffs, times):
+        coeffs = self._r(coeffs)
+        times = self._r(times)
+        return self.lib.orc_compute_cost(N, K, D, derivative, self._p(coeffs), self._p(times))
+
+    # -- evaluation ----------------------------------------------------------------
+    def polynomial_evaluate(self, c, t, derivative):
+        c = self._r(c)
+        return self.lib.orc_polynomial_evaluate(C.c_int(c.shape[0]), self._p(c), self.creal(t), C.c_int(derivative))
+
+    def trajectory_evaluate(self, coeffs, times, t, derivative):
+        coeffs = self._r(coeffs)
+        K, D, N = coeffs.shape
+        times = self._r(times)
+        out = np.zeros(D, self.real)
+        seg = self.lib.orc_trajectory_evaluate(N, K, D, self._p(coeffs), self._p(times), self.creal(t),
+                                               C.c_int(derivative), self._p(out))
+        return out, seg
+
+    def trajectory_sample(self, coeffs, times, t, n_deriv):
+        coeffs = self._r(coeffs)
+        K, D, N = coeffs.shape
+        times = self._r(times)
+        t = self._r(t)
+        M = t.shape[0]
+        out = np.zeros((M, n_deriv, D), self.real)
+        self.lib.orc_trajectory_sample(N, K, D, self._p(coeffs), self._p(times), M, self._p(t), n_deriv, self._p(out))
+        return out
+
+    def trajectory_evaluate_range(self, coeffs, times, t_start, t_end, dt, derivative, max_out=1 << 20):
+        coeffs = self._r(coeffs)
+        K, D, N = coeffs.shape
+        times = self._r(times)
+        out = np.zeros((max_out, D), self.real)
+        st = np.zeros(max_out, self.real)
+        n = self.lib.orc_trajectory_evaluate_range(N, K, D, self._p(coeffs), self._p(times), self.creal(t_start),
+                                                   self.creal(t_end), self.creal(dt), C.c_int(derivative),
+                                                   C.c_int(max_out), self._p(out), self._p(st))
+        n = min(n, max_out)
+        return out[:n].copy(), st[:n].copy()
+
+    # -- inputs --------------------------------------------------------------------
+    def estimate_segment_times(self, positions, v_max, a_max, magic=6.5):
+        positions = self._r(positions)
+        K = positions.shape[0] - 1
+        D = positions.shape[1]
+        times = np.zeros(K, self.real)
+        self.lib.orc_estimate_segment_times(K, D, self._p(positions), self.creal(v_max), self.creal(a_max),
+                                            self.creal(magic), self._p(times))
+        return times
+
+    def create_random_positions(self, K, pos_min, pos_max, seed):
+        pos_min = np.ascontiguousarray(np.asarray(pos_min, np.float64))
+        pos_max = np.ascontiguousarray(np.asarray(pos_max, np.float64))
+        D = pos_min.shape[0]
+        out = np.zeros((K + 1, D), np.float64)
+        self.lib.orc_create_random_positions(K, D, self._p(pos_min), self._p(pos_max), C.c_uint64(seed), self._p(out))
+        return out
+
+    def mt19937_uniform(self, seed, a, b, n):
+        out = np.zeros(n, np.float64)
+        self.lib.orc_mt19937_uniform(C.c_uint64(seed), C.c_double(a), C.c_double(b), n, self._p(out))
+        return out
+
+    # -- CPU baseline --------------------------------------------------------------
+    def solve_batch_standard(self, positions, times, N=10, derivative=4, max_fixed_derivative=4,
+                             n_threads=1, want_coeffs=True):
+        """positions[B][K+1][D], times[B][K] (float64) -> coeffs[B][K][D][N], cost[B], status."""
+        assert self.precision == "f64"
+        positions = np.ascontiguousarray(positions, np.float64)
+        times = np.ascontiguousarray(times, np.float64)
+        B, K1, D = positions.shape
+        K = K1 - 1
+        coeffs = np.zeros((B, K, D, N), np.float64) if want_coeffs else None
+        cost = np.zeros(B, np.float64)
+        st = self.lib.orc_solve_batch_standard(N, K, D, derivative, max_fixed_derivative, C.c_long(B),
+                                               self._p(positions), self._p(times),
+                                               self._p(coeffs) if want_coeffs else None, self._p(cost),
+                                               C.c_int(n_threads))
+        return coeffs, cost, st
+
+
+def standard_mask(K, N=10, max_fixed_derivative=4):
+    """Mask produced by createRandomVertices (src/vertex.cpp:59,71-76): end vertices fix
+    derivatives 0..max_fixed_derivative, interior vertices fix position only."""
+    h = N // 2
+    m = np.zeros((K + 1, h), np.uint8)
+    m[:, 0] = 1
+    m[0, : max_fixed_derivative + 1] = 1
+    m[K, : max_fixed_derivative + 1] = 1
+    return m
+
+
+def vertex_values_from_positions(positions, N=10):
+    """[K+1][D] positions -> [K+1][N/2][D] constraint-value table (derivatives zero)."""
+    positions = np.asarray(positions)
+    K1, D = positions.shape
+    v = np.zeros((K1, N // 2, D), positions.dtype)
+    v[:, 0, :] = positions
+    return v
