@@ -1,0 +1,368 @@
+"""Python plumbing over the C ABI: torch tensors for device memory and streams, numpy arrays
+for the host-buffer entry points.  Every function is a thin argument marshaller around one
+C-ABI call -- there is no arithmetic and no fallback here.
+
+Layouts are those of include/minsnap_b200.h (h = N/2):
+  fixed_values [B][n_fixed][D], free_values [B][n_free][D], positions [B][K+1][D],
+  times [B][K], coeffs [B][K][D][N], samples [B][M][n_deriv][D].
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+SNAP = 4
+
+
+def _lib():
+    return capi.load()
+
+
+# ------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------
+def _torch():
+    import torch
+    return torch
+
+
+def _dptr(t, dtype=None):
+    if t is None:
+        return None
+    torch = _torch()
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    if dtype is not None:
+        assert t.dtype == dtype, "expected dtype %s, got %s" % (dtype, t.dtype)
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _hptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _np(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+def standard_mask(K, N=10, max_fixed_derivative=None):
+    """Mask of createRandomVertices (ref src/vertex.cpp:59,71-76)."""
+    h = N // 2
+    if max_fixed_derivative is None:
+        max_fixed_derivative = h - 1
+    m = np.zeros((K + 1, h), np.uint8)
+    m[:, 0] = 1
+    m[0, : max_fixed_derivative + 1] = 1
+    m[K, : max_fixed_derivative + 1] = 1
+    return m
+
+
+def mask_counts(mask):
+    mask = np.asarray(mask)
+    n_fixed = int((mask != 0).sum())
+    return n_fixed, mask.size - n_fixed
+
+
+def device_info():
+    dev, sms, maj, mnr = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    mem = C.c_size_t()
+    capi.check(_lib().minsnap_device_info(C.byref(dev), C.byref(sms), C.byref(maj), C.byref(mnr), C.byref(mem)),
+               "minsnap_device_info")
+    return dict(device=dev.value, sm_count=sms.value, cc=(maj.value, mnr.value), global_mem_bytes=mem.value)
+
+
+def fp64_peak(repeats=5):
+    out = C.c_double()
+    capi.check(_lib().minsnap_fp64_peak(repeats, C.byref(out)), "minsnap_fp64_peak")
+    return out.value
+
+
+# ------------------------------------------------------------------------------------------
+# device-pointer entry points (torch CUDA tensors, current stream, asynchronous)
+# ------------------------------------------------------------------------------------------
+def reorder(mask_dev, N, K):
+    """mask_dev uint8 [n_masks][(K+1)*h] on the GPU -> (col_of_row int32 [n_masks][N*K], counts int32 [n_masks][2])."""
+    torch = _torch()
+    n_masks = mask_dev.shape[0]
+    col = torch.empty((n_masks, N * K), dtype=torch.int32, device=mask_dev.device)
+    counts = torch.empty((n_masks, 2), dtype=torch.int32, device=mask_dev.device)
+    capi.check(_lib().minsnap_reorder(N, K, n_masks, _dptr(mask_dev, torch.uint8), _dptr(col), _dptr(counts), _stream()),
+               "minsnap_reorder")
+    return col, counts
+
+
+def estimate_segment_times(positions, v_max, a_max, magic=6.5):
+    torch = _torch()
+    B, K1, D = positions.shape
+    times = torch.empty((B, K1 - 1), dtype=torch.float64, device=positions.device)
+    capi.check(_lib().minsnap_estimate_segment_times(B, K1 - 1, D, _dptr(positions, torch.float64), v_max, a_max, magic,
+                                                     _dptr(times), _stream()), "minsnap_estimate_segment_times")
+    return times
+
+
+def segment_matrices(T, N=10, derivative=SNAP):
+    """T float64 [n] on the GPU -> dict(A, Ainv, Q, H), each [n][N][N]."""
+    torch = _torch()
+    n = T.shape[0]
+    out = {k: torch.empty((n, N, N), dtype=torch.float64, device=T.device) for k in ("A", "Ainv", "Q", "H")}
+    capi.check(_lib().minsnap_segment_matrices(n, N, derivative, _dptr(T, torch.float64), _dptr(out["A"]),
+                                               _dptr(out["Ainv"]), _dptr(out["Q"]), _dptr(out["H"]), _stream()),
+               "minsnap_segment_matrices")
+    return out
+
+
+def solve(mask, fixed_values, times, N=10, derivative=SNAP, want_cost=True):
+    """General batched setupFromVertices + solveLinear.  mask: host uint8 [(K+1)][h]."""
+    torch = _torch()
+    mask = np.ascontiguousarray(mask, np.uint8)
+    K = mask.shape[0] - 1
+    B, n_fixed, D = fixed_values.shape
+    nf, n_free = mask_counts(mask)
+    assert nf == n_fixed and times.shape == (B, K)
+    dev = times.device
+    coeffs = torch.empty((B, K, D, N), dtype=torch.float64, device=dev)
+    free = torch.empty((B, n_free, D), dtype=torch.float64, device=dev)
+    cost = torch.empty((B,), dtype=torch.float64, device=dev) if want_cost else None
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    col = torch.empty((N * K,), dtype=torch.int32, device=dev)
+    ws_bytes = _lib().minsnap_solve_workspace_bytes(N, K)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    capi.check(_lib().minsnap_solve(B, K, D, N, derivative, _hptr(mask), _dptr(fixed_values, torch.float64),
+                                    _dptr(times, torch.float64), _dptr(coeffs), _dptr(free), _dptr(cost), _dptr(status),
+                                    _dptr(col), _dptr(ws), ws_bytes, _stream()), "minsnap_solve")
+    return dict(coeffs=coeffs, free_values=free, cost=cost, status=status, col_of_row=col)
+
+
+def coeffs_from_constraints(mask, fixed_values, free_values, times, N=10):
+    torch = _torch()
+    mask = np.ascontiguousarray(mask, np.uint8)
+    K = mask.shape[0] - 1
+    B, _, D = fixed_values.shape
+    coeffs = torch.empty((B, K, D, N), dtype=torch.float64, device=times.device)
+    ws_bytes = _lib().minsnap_solve_workspace_bytes(N, K)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=times.device)
+    capi.check(_lib().minsnap_coeffs_from_constraints(B, K, D, N, _hptr(mask), _dptr(fixed_values), _dptr(free_values),
+                                                      _dptr(times), _dptr(coeffs), _dptr(ws), ws_bytes, _stream()),
+               "minsnap_coeffs_from_constraints")
+    return coeffs
+
+
+def cost(coeffs, times, derivative=SNAP):
+    torch = _torch()
+    B, K, D, N = coeffs.shape
+    out = torch.empty((B,), dtype=torch.float64, device=coeffs.device)
+    capi.check(_lib().minsnap_cost(B, K, D, N, derivative, _dptr(coeffs, torch.float64), _dptr(times, torch.float64),
+                                   _dptr(out), _stream()), "minsnap_cost")
+    return out
+
+
+def solve_standard(positions, times=None, end_derivatives=None, v_max=0.0, a_max=0.0, magic=6.5, N=10,
+                   derivative=SNAP, coeffs=None, want_free=False, want_cost=False, want_status=True,
+                   want_times=False):
+    """Standard-mask batched solve.  times=None => estimated on the device from (v_max, a_max, magic)."""
+    torch = _torch()
+    B, K1, D = positions.shape
+    K = K1 - 1
+    h = N // 2
+    dev = positions.device
+    if coeffs is None:
+        coeffs = torch.empty((B, K, D, N), dtype=torch.float64, device=dev)
+    free = torch.empty((B, (K - 1) * (h - 1), D), dtype=torch.float64, device=dev) if want_free else None
+    cost_t = torch.empty((B,), dtype=torch.float64, device=dev) if want_cost else None
+    status = torch.empty((B,), dtype=torch.int32, device=dev) if want_status else None
+    times_out = torch.empty((B, K), dtype=torch.float64, device=dev) if (want_times and times is None) else None
+    capi.check(_lib().minsnap_solve_standard(B, K, D, N, derivative, _dptr(positions, torch.float64),
+                                             _dptr(end_derivatives), _dptr(times), v_max, a_max, magic,
+                                             _dptr(times_out), _dptr(coeffs), _dptr(free), _dptr(cost_t), _dptr(status),
+                                             _stream()), "minsnap_solve_standard")
+    return dict(coeffs=coeffs, free_values=free, cost=cost_t, status=status,
+                times=times if times is not None else times_out)
+
+
+def sample_uniform(coeffs, times, M, n_deriv=5, out=None, want_times=False):
+    torch = _torch()
+    B, K, D, N = coeffs.shape
+    if out is None:
+        out = torch.empty((B, M, n_deriv, D), dtype=torch.float64, device=coeffs.device)
+    t_out = torch.empty((B, M), dtype=torch.float64, device=coeffs.device) if want_times else None
+    capi.check(_lib().minsnap_sample_uniform(B, K, D, N, _dptr(coeffs, torch.float64), _dptr(times, torch.float64), M,
+                                             n_deriv, _dptr(out), _dptr(t_out), _stream()), "minsnap_sample_uniform")
+    return (out, t_out) if want_times else out
+
+
+def sample_at(coeffs, times, t, n_deriv=5, want_segment=False):
+    """t: [B][M] per-trajectory instants or [M] shared by the whole batch."""
+    torch = _torch()
+    B, K, D, N = coeffs.shape
+    M = t.shape[-1]
+    stride = 0 if t.dim() == 1 else M
+    out = torch.empty((B, M, n_deriv, D), dtype=torch.float64, device=coeffs.device)
+    seg = torch.empty((B, M), dtype=torch.int32, device=coeffs.device) if want_segment else None
+    capi.check(_lib().minsnap_sample_at(B, K, D, N, _dptr(coeffs, torch.float64), _dptr(times, torch.float64), M,
+                                        _dptr(t, torch.float64), stride, n_deriv, _dptr(out), _dptr(seg), _stream()),
+               "minsnap_sample_at")
+    return (out, seg) if want_segment else out
+
+
+def evaluate_range(coeffs, times, t_start, t_end, dt, derivative, max_samples):
+    torch = _torch()
+    B, K, D, N = coeffs.shape
+    out = torch.zeros((B, max_samples, D), dtype=torch.float64, device=coeffs.device)
+    t_out = torch.zeros((B, max_samples), dtype=torch.float64, device=coeffs.device)
+    count = torch.zeros((B,), dtype=torch.int32, device=coeffs.device)
+    capi.check(_lib().minsnap_evaluate_range(B, K, D, N, _dptr(coeffs, torch.float64), _dptr(times, torch.float64),
+                                             t_start, t_end, dt, derivative, max_samples, _dptr(out), _dptr(t_out),
+                                             _dptr(count), _stream()), "minsnap_evaluate_range")
+    return out, t_out, count
+
+
+def cost_sweep(positions, times, end_derivatives=None, N=10, derivative=SNAP, want_status=False):
+    """positions [B][K+1][D], times [B][S][K] -> cost [B][S]."""
+    torch = _torch()
+    B, K1, D = positions.shape
+    S = times.shape[1]
+    out = torch.empty((B, S), dtype=torch.float64, device=positions.device)
+    status = torch.empty((B, S), dtype=torch.int32, device=positions.device) if want_status else None
+    capi.check(_lib().minsnap_cost_sweep(B, S, K1 - 1, D, N, derivative, _dptr(positions, torch.float64),
+                                         _dptr(end_derivatives), _dptr(times, torch.float64), _dptr(out), _dptr(status),
+                                         _stream()), "minsnap_cost_sweep")
+    return (out, status) if want_status else out
+
+
+# ------------------------------------------------------------------------------------------
+# host-buffer entry points (numpy arrays, synchronous, copies inside)
+# ------------------------------------------------------------------------------------------
+def solve_host(mask, fixed_values, times, N=10, derivative=SNAP):
+    mask = np.ascontiguousarray(mask, np.uint8)
+    K = mask.shape[0] - 1
+    fixed_values = _np(fixed_values, np.float64)
+    times = _np(times, np.float64)
+    B, n_fixed, D = fixed_values.shape
+    _, n_free = mask_counts(mask)
+    coeffs = np.empty((B, K, D, N), np.float64)
+    free = np.empty((B, n_free, D), np.float64)
+    cost_a = np.empty((B,), np.float64)
+    status = np.empty((B,), np.int32)
+    col = np.empty((N * K,), np.int32)
+    capi.check(_lib().minsnap_solve_host(B, K, D, N, derivative, _hptr(mask), _hptr(fixed_values), _hptr(times),
+                                         _hptr(coeffs), _hptr(free), _hptr(cost_a), _hptr(status), _hptr(col)),
+               "minsnap_solve_host")
+    return dict(coeffs=coeffs, free_values=free, cost=cost_a, status=status, col_of_row=col)
+
+
+def solve_standard_host(positions, times=None, end_derivatives=None, v_max=0.0, a_max=0.0, magic=6.5, N=10,
+                        derivative=SNAP, coeffs=None, want_free=False, want_cost=False, want_status=False):
+    """positions/times/coeffs may be numpy arrays or pinned CPU torch tensors (zero-copy)."""
+    def host(a):
+        if a is None:
+            return None, None
+        if isinstance(a, np.ndarray):
+            a = np.ascontiguousarray(a, np.float64)
+            return a, a.ctypes.data_as(C.c_void_p)
+        assert not a.is_cuda and a.is_contiguous()
+        return a, C.c_void_p(a.data_ptr())
+
+    positions, p_pos = host(positions)
+    times, p_t = host(times)
+    end_derivatives, p_end = host(end_derivatives)
+    B, K1, D = positions.shape
+    K = K1 - 1
+    h = N // 2
+    if coeffs is None:
+        coeffs = np.empty((B, K, D, N), np.float64)
+    coeffs, p_c = host(coeffs)
+    free = np.empty((B, (K - 1) * (h - 1), D), np.float64) if want_free else None
+    cost_a = np.empty((B,), np.float64) if want_cost else None
+    status = np.empty((B,), np.int32) if want_status else None
+    times_out = np.empty((B, K), np.float64) if times is None else None
+    capi.check(_lib().minsnap_solve_standard_host(B, K, D, N, derivative, p_pos, p_end, p_t, v_max, a_max, magic,
+                                                  _hptr(times_out), p_c, _hptr(free), _hptr(cost_a), _hptr(status)),
+               "minsnap_solve_standard_host")
+    return dict(coeffs=coeffs, free_values=free, cost=cost_a, status=status,
+                times=times if times is not None else times_out)
+
+
+def sample_at_host(coeffs, times, t, n_deriv=5):
+    coeffs = _np(coeffs, np.float64)
+    times = _np(times, np.float64)
+    t = _np(t, np.float64)
+    B, K, D, N = coeffs.shape
+    M = t.shape[-1]
+    stride = 0 if t.ndim == 1 else M
+    out = np.empty((B, M, n_deriv, D), np.float64)
+    seg = np.empty((B, M), np.int32)
+    capi.check(_lib().minsnap_sample_at_host(B, K, D, N, _hptr(coeffs), _hptr(times), M, _hptr(t), stride, n_deriv,
+                                             _hptr(out), _hptr(seg)), "minsnap_sample_at_host")
+    return out, seg
+
+
+def evaluate_range_host(coeffs, times, t_start, t_end, dt, derivative, max_samples=1 << 16):
+    coeffs = _np(coeffs, np.float64)
+    times = _np(times, np.float64)
+    K, D, N = coeffs.shape
+    out = np.zeros((max_samples, D), np.float64)
+    t_out = np.zeros((max_samples,), np.float64)
+    count = C.c_int32()
+    capi.check(_lib().minsnap_evaluate_range_host(K, D, N, _hptr(coeffs), _hptr(times), t_start, t_end, dt, derivative,
+                                                  max_samples, _hptr(out), _hptr(t_out), C.byref(count)),
+               "minsnap_evaluate_range_host")
+    n = min(count.value, max_samples)
+    return out[:n].copy(), t_out[:n].copy(), count.value
+
+
+def segment_matrices_host(T, N=10, derivative=SNAP):
+    T = _np(np.atleast_1d(T), np.float64)
+    n = T.shape[0]
+    out = {k: np.empty((n, N, N), np.float64) for k in ("A", "Ainv", "Q", "H")}
+    capi.check(_lib().minsnap_segment_matrices_host(n, N, derivative, _hptr(T), _hptr(out["A"]), _hptr(out["Ainv"]),
+                                                    _hptr(out["Q"]), _hptr(out["H"])), "minsnap_segment_matrices_host")
+    return out
+
+
+def estimate_segment_times_host(positions, v_max, a_max, magic=6.5):
+    positions = _np(positions, np.float64)
+    B, K1, D = positions.shape
+    times = np.empty((B, K1 - 1), np.float64)
+    capi.check(_lib().minsnap_estimate_segment_times_host(B, K1 - 1, D, _hptr(positions), v_max, a_max, magic,
+                                                          _hptr(times)), "minsnap_estimate_segment_times_host")
+    return times
+
+
+def coeffs_from_constraints_host(mask, fixed_values, free_values, times, N=10):
+    mask = np.ascontiguousarray(mask, np.uint8)
+    K = mask.shape[0] - 1
+    fixed_values = _np(fixed_values, np.float64)
+    free_values = _np(free_values, np.float64)
+    times = _np(times, np.float64)
+    B, _, D = fixed_values.shape
+    coeffs = np.empty((B, K, D, N), np.float64)
+    capi.check(_lib().minsnap_coeffs_from_constraints_host(B, K, D, N, _hptr(mask), _hptr(fixed_values),
+                                                           _hptr(free_values), _hptr(times), _hptr(coeffs)),
+               "minsnap_coeffs_from_constraints_host")
+    return coeffs
+
+
+def cost_host(coeffs, times, derivative=SNAP):
+    coeffs = _np(coeffs, np.float64)
+    times = _np(times, np.float64)
+    B, K, D, N = coeffs.shape
+    out = np.empty((B,), np.float64)
+    capi.check(_lib().minsnap_cost_host(B, K, D, N, derivative, _hptr(coeffs), _hptr(times), _hptr(out)),
+               "minsnap_cost_host")
+    return out
+
+
+def random_positions_host(B, K, pos_min, pos_max, base_seed):
+    """Batched createRandomVertices positions (host-only workload generator): [B][K+1][D]."""
+    pos_min = _np(pos_min, np.float64)
+    pos_max = _np(pos_max, np.float64)
+    D = pos_min.shape[0]
+    out = np.empty((B, K + 1, D), np.float64)
+    capi.check(_lib().minsnap_random_positions_host(B, K, D, _hptr(pos_min), _hptr(pos_max), base_seed, _hptr(out)),
+               "minsnap_random_positions_host")
+    return out

@@ -1,0 +1,613 @@
+// C ABI of libminsnap_b200.so (declared in include/minsnap_b200.h): argument checking,
+// workspace carving, stream-ordered scratch memory and the host-buffer pipelines.  No
+// arithmetic of the hot path happens here -- every number comes out of a CUDA kernel.
+#include "../../include/minsnap_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "minsnap_launch.h"
+
+namespace {
+
+thread_local char g_last_cuda_error[256] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+  std::snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s (%s)", what, cudaGetErrorName(e),
+                cudaGetErrorString(e));
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return MINSNAP_ERR_NO_DEVICE;
+  if (e == cudaErrorInvalidConfiguration) return MINSNAP_ERR_UNSUPPORTED;
+  return MINSNAP_ERR_CUDA;
+}
+
+#define CU(call)                                        \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+inline cudaStream_t as_stream(minsnap_stream_t s) { return static_cast<cudaStream_t>(s); }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct SolveWorkspace {
+  uint8_t* mask;
+  int32_t* col_of_row;
+  int32_t* counts;
+  static size_t bytes(int N, int K) {
+    return align_up((size_t)(K + 1) * (N / 2), 16) + align_up(sizeof(int32_t) * (size_t)N * K, 16) + 16;
+  }
+  SolveWorkspace(void* base, int N, int K) {
+    char* p = static_cast<char*>(base);
+    mask = reinterpret_cast<uint8_t*>(p);
+    p += align_up((size_t)(K + 1) * (N / 2), 16);
+    col_of_row = reinterpret_cast<int32_t*>(p);
+    p += align_up(sizeof(int32_t) * (size_t)N * K, 16);
+    counts = reinterpret_cast<int32_t*>(p);
+  }
+};
+
+bool shape_ok(long B, int K, int D, int N, int derivative) {
+  return B >= 0 && K >= 1 && D >= 1 && minsnap::supported_n(N) && derivative >= 0 && derivative <= N / 2 - 1;
+}
+
+void count_mask(const uint8_t* mask, int N, int K, int* n_fixed, int* n_free) {
+  int f = 0;
+  const int nc = (K + 1) * (N / 2);
+  for (int i = 0; i < nc; ++i) f += mask[i] != 0;
+  *n_fixed = f;
+  *n_free = nc - f;
+}
+
+// Stream-ordered scratch buffer (cudaMallocAsync); freed on the same stream.
+struct Scratch {
+  void* ptr = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaError_t alloc(size_t bytes, cudaStream_t s) {
+    stream = s;
+    if (bytes == 0) bytes = 16;
+    return cudaMallocAsync(&ptr, bytes, s);
+  }
+  ~Scratch() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(ptr); }
+};
+
+// Keep freed scratch memory in the device pool so that repeated host-API calls do not pay
+// for cudaMalloc each time.
+void retain_pool_memory() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
+  uint64_t threshold = ~0ull;
+  cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+}
+
+struct StreamPair {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaError_t create() {
+    for (auto& st : s) {
+      cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  ~StreamPair() {
+    for (auto st : s)
+      if (st) cudaStreamDestroy(st);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int minsnap_abi_version(void) { return 1; }
+
+const char* minsnap_error_string(int code) {
+  switch (code) {
+    case MINSNAP_OK: return "ok";
+    case MINSNAP_ERR_ARG: return "invalid argument";
+    case MINSNAP_ERR_CUDA: return "CUDA runtime error";
+    case MINSNAP_ERR_UNSUPPORTED: return "unsupported shape";
+    case MINSNAP_ERR_NO_DEVICE: return "no usable CUDA device";
+    case MINSNAP_ERR_WORKSPACE: return "workspace missing or too small";
+    default: return "unknown error";
+  }
+}
+
+const char* minsnap_last_cuda_error(void) { return g_last_cuda_error; }
+
+int minsnap_device_info(int* device, int* sm_count, int* cc_major, int* cc_minor, size_t* global_mem_bytes) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (n == 0) return MINSNAP_ERR_NO_DEVICE;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  if (device) *device = dev;
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (global_mem_bytes) *global_mem_bytes = prop.totalGlobalMem;
+  return MINSNAP_OK;
+}
+
+int minsnap_reorder(int N, int K, long n_masks, const uint8_t* d_mask, int32_t* d_col_of_row, int32_t* d_counts,
+                    minsnap_stream_t stream) {
+  if (!minsnap::supported_n(N) || K < 1 || n_masks < 0 || !d_mask || !d_col_of_row || !d_counts)
+    return MINSNAP_ERR_ARG;
+  if (n_masks == 0) return MINSNAP_OK;
+  CU(minsnap::launch_reorder(N, K, n_masks, d_mask, d_col_of_row, d_counts, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
+int minsnap_estimate_segment_times(long B, int K, int D, const double* d_positions, double v_max, double a_max,
+                                   double magic, double* d_times, minsnap_stream_t stream) {
+  if (B < 0 || K < 1 || D < 1 || !d_positions || !d_times) return MINSNAP_ERR_ARG;
+  CU(minsnap::launch_estimate_times(B, K, D, d_positions, v_max, a_max, magic, d_times, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
+int minsnap_segment_matrices(long n, int N, int derivative, const double* d_T, double* d_A, double* d_Ainv,
+                             double* d_Q, double* d_H, minsnap_stream_t stream) {
+  if (n < 0 || !minsnap::supported_n(N) || derivative < 0 || derivative > N / 2 - 1 || !d_T) return MINSNAP_ERR_ARG;
+  CU(minsnap::launch_segment_matrices(n, N, derivative, d_T, d_A, d_Ainv, d_Q, d_H, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
+size_t minsnap_solve_workspace_bytes(int N, int K) {
+  if (!minsnap::supported_n(N) || K < 1) return 0;
+  return SolveWorkspace::bytes(N, K);
+}
+
+static int general_common(bool solve, long B, int K, int D, int N, int derivative, const uint8_t* h_fixed_mask,
+                          const double* d_fixed_values, const double* d_free_in, const double* d_times,
+                          double* d_coeffs, double* d_free_out, double* d_cost, int32_t* d_status,
+                          int32_t* d_col_of_row, void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!shape_ok(B, K, D, N, derivative) || !h_fixed_mask || !d_times || !d_coeffs) return MINSNAP_ERR_ARG;
+  if (!d_workspace || workspace_bytes < SolveWorkspace::bytes(N, K)) return MINSNAP_ERR_WORKSPACE;
+  int n_fixed, n_free;
+  count_mask(h_fixed_mask, N, K, &n_fixed, &n_free);
+  if (n_fixed > 0 && !d_fixed_values) return MINSNAP_ERR_ARG;
+  if (!solve && n_free > 0 && !d_free_in) return MINSNAP_ERR_ARG;
+  SolveWorkspace ws(d_workspace, N, K);
+  CU(cudaMemcpyAsync(ws.mask, h_fixed_mask, (size_t)(K + 1) * (N / 2), cudaMemcpyHostToDevice, stream));
+  CU(minsnap::launch_reorder(N, K, 1, ws.mask, ws.col_of_row, ws.counts, stream));
+  if (d_col_of_row)
+    CU(cudaMemcpyAsync(d_col_of_row, ws.col_of_row, sizeof(int32_t) * (size_t)N * K, cudaMemcpyDeviceToDevice,
+                       stream));
+  minsnap::GeneralSolveArgs a;
+  a.B = B; a.K = K; a.D = D; a.N = N; a.derivative = derivative; a.n_fixed = n_fixed; a.n_free = n_free;
+  a.d_col_of_row = ws.col_of_row; a.d_fixed_values = d_fixed_values; a.d_free_in = d_free_in;
+  a.d_times = d_times; a.d_coeffs = d_coeffs; a.d_free_out = d_free_out; a.d_cost = d_cost;
+  a.d_status = d_status;
+  if (solve) CU(minsnap::launch_solve_general(a, stream));
+  else CU(minsnap::launch_coeffs_from_constraints(a, stream));
+  return MINSNAP_OK;
+}
+
+int minsnap_solve(long B, int K, int D, int N, int derivative, const uint8_t* h_fixed_mask,
+                  const double* d_fixed_values, const double* d_times, double* d_coeffs, double* d_free_values,
+                  double* d_cost, int32_t* d_status, int32_t* d_col_of_row, void* d_workspace,
+                  size_t workspace_bytes, minsnap_stream_t stream) {
+  return general_common(true, B, K, D, N, derivative, h_fixed_mask, d_fixed_values, nullptr, d_times, d_coeffs,
+                        d_free_values, d_cost, d_status, d_col_of_row, d_workspace, workspace_bytes,
+                        as_stream(stream));
+}
+
+int minsnap_coeffs_from_constraints(long B, int K, int D, int N, const uint8_t* h_fixed_mask,
+                                    const double* d_fixed_values, const double* d_free_values,
+                                    const double* d_times, double* d_coeffs, void* d_workspace,
+                                    size_t workspace_bytes, minsnap_stream_t stream) {
+  return general_common(false, B, K, D, N, 0, h_fixed_mask, d_fixed_values, d_free_values, d_times, d_coeffs,
+                        nullptr, nullptr, nullptr, nullptr, d_workspace, workspace_bytes, as_stream(stream));
+}
+
+int minsnap_cost(long B, int K, int D, int N, int derivative, const double* d_coeffs, const double* d_times,
+                 double* d_cost, minsnap_stream_t stream) {
+  if (!shape_ok(B, K, D, N, derivative) || !d_coeffs || !d_times || !d_cost) return MINSNAP_ERR_ARG;
+  CU(minsnap::launch_cost(B, K, D, N, derivative, d_coeffs, d_times, d_cost, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
+int minsnap_solve_standard(long B, int K, int D, int N, int derivative, const double* d_positions,
+                           const double* d_end_derivatives, const double* d_times, double v_max, double a_max,
+                           double magic, double* d_times_out, double* d_coeffs, double* d_free_values,
+                           double* d_cost, int32_t* d_status, minsnap_stream_t stream) {
+  if (!shape_ok(B, K, D, N, derivative) || !d_positions || !d_coeffs) return MINSNAP_ERR_ARG;
+  if (!d_times && !(v_max > 0.0 && a_max > 0.0)) return MINSNAP_ERR_ARG;
+  minsnap::StandardSolveArgs a;
+  a.B = B; a.K = K; a.D = D; a.N = N; a.derivative = derivative;
+  a.d_positions = d_positions; a.d_end_derivatives = d_end_derivatives; a.d_times = d_times;
+  a.v_max = v_max; a.a_max = a_max; a.magic = magic; a.d_times_out = d_times_out;
+  a.d_coeffs = d_coeffs; a.d_free_out = d_free_values; a.d_cost = d_cost; a.d_status = d_status;
+  CU(minsnap::launch_solve_standard(a, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
+int minsnap_sample_uniform(long B, int K, int D, int N, const double* d_coeffs, const double* d_times, int M,
+                           int n_deriv, double* d_out, double* d_t_out, minsnap_stream_t stream) {
+  if (B < 0 || K < 1 || D < 1 || !minsnap::supported_n(N) || M < 0 || n_deriv < 1 || !d_coeffs || !d_times ||
+      !d_out)
+    return MINSNAP_ERR_ARG;
+  minsnap::SampleArgs a;
+  a.B = B; a.K = K; a.D = D; a.N = N; a.M = M; a.n_deriv = n_deriv;
+  a.d_coeffs = d_coeffs; a.d_times = d_times; a.d_t = nullptr; a.t_stride = 0;
+  a.d_out = d_out; a.d_t_out = d_t_out; a.d_segment = nullptr;
+  CU(minsnap::launch_sample(a, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
+int minsnap_sample_at(long B, int K, int D, int N, const double* d_coeffs, const double* d_times, int M,
+                      const double* d_t, long t_stride, int n_deriv, double* d_out, int32_t* d_segment,
+                      minsnap_stream_t stream) {
+  if (B < 0 || K < 1 || D < 1 || !minsnap::supported_n(N) || M < 0 || n_deriv < 1 || !d_coeffs || !d_times ||
+      !d_t || !d_out || (t_stride != 0 && t_stride < M))
+    return MINSNAP_ERR_ARG;
+  minsnap::SampleArgs a;
+  a.B = B; a.K = K; a.D = D; a.N = N; a.M = M; a.n_deriv = n_deriv;
+  a.d_coeffs = d_coeffs; a.d_times = d_times; a.d_t = d_t; a.t_stride = t_stride;
+  a.d_out = d_out; a.d_t_out = nullptr; a.d_segment = d_segment;
+  CU(minsnap::launch_sample(a, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
+int minsnap_evaluate_range(long B, int K, int D, int N, const double* d_coeffs, const double* d_times,
+                           double t_start, double t_end, double dt, int derivative, int max_samples,
+                           double* d_out, double* d_t_out, int32_t* d_count, minsnap_stream_t stream) {
+  if (B < 0 || K < 1 || D < 1 || !minsnap::supported_n(N) || !(dt > 0.0) || derivative < 0 || max_samples < 0 ||
+      !d_coeffs || !d_times || !d_out)
+    return MINSNAP_ERR_ARG;
+  CU(minsnap::launch_evaluate_range(B, K, D, N, d_coeffs, d_times, t_start, t_end, dt, derivative, max_samples,
+                                    d_out, d_t_out, d_count, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
+int minsnap_cost_sweep(long B, int S, int K, int D, int N, int derivative, const double* d_positions,
+                       const double* d_end_derivatives, const double* d_times, double* d_cost, int32_t* d_status,
+                       minsnap_stream_t stream) {
+  if (!shape_ok(B, K, D, N, derivative) || S < 1 || !d_positions || !d_times || !d_cost) return MINSNAP_ERR_ARG;
+  minsnap::SweepArgs a;
+  a.B = B; a.S = S; a.K = K; a.D = D; a.N = N; a.derivative = derivative;
+  a.d_positions = d_positions; a.d_end_derivatives = d_end_derivatives; a.d_times = d_times;
+  a.d_cost = d_cost; a.d_status = d_status;
+  CU(minsnap::launch_cost_sweep(a, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Host-buffer entry points
+// ---------------------------------------------------------------------------------------
+int minsnap_host_alloc(void** h_ptr, size_t bytes) {
+  if (!h_ptr) return MINSNAP_ERR_ARG;
+  CU(cudaHostAlloc(h_ptr, bytes ? bytes : 16, cudaHostAllocDefault));
+  return MINSNAP_OK;
+}
+
+int minsnap_host_free(void* h_ptr) {
+  if (!h_ptr) return MINSNAP_OK;
+  CU(cudaFreeHost(h_ptr));
+  return MINSNAP_OK;
+}
+
+int minsnap_solve_host(long B, int K, int D, int N, int derivative, const uint8_t* h_fixed_mask,
+                       const double* h_fixed_values, const double* h_times, double* h_coeffs,
+                       double* h_free_values, double* h_cost, int32_t* h_status, int32_t* h_col_of_row) {
+  if (!shape_ok(B, K, D, N, derivative) || !h_fixed_mask || !h_times || !h_coeffs) return MINSNAP_ERR_ARG;
+  int n_fixed, n_free;
+  count_mask(h_fixed_mask, N, K, &n_fixed, &n_free);
+  if (n_fixed > 0 && !h_fixed_values) return MINSNAP_ERR_ARG;
+  retain_pool_memory();
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = MINSNAP_OK;
+  {
+    Scratch fv, tm, co, fr, cs, ss, ws, cr;
+    const size_t nb = (size_t)B;
+#define TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #x); goto done; } } while (0)
+    TRY(fv.alloc(sizeof(double) * nb * n_fixed * D, st));
+    TRY(tm.alloc(sizeof(double) * nb * K, st));
+    TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
+    TRY(fr.alloc(sizeof(double) * nb * n_free * D, st));
+    TRY(cs.alloc(sizeof(double) * nb, st));
+    TRY(ss.alloc(sizeof(int32_t) * nb, st));
+    TRY(cr.alloc(sizeof(int32_t) * (size_t)N * K, st));
+    TRY(ws.alloc(SolveWorkspace::bytes(N, K), st));
+    if (n_fixed > 0)
+      TRY(cudaMemcpyAsync(fv.ptr, h_fixed_values, sizeof(double) * nb * n_fixed * D, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
+    rc = minsnap_solve(B, K, D, N, derivative, h_fixed_mask, fv.as<double>(), tm.as<double>(), co.as<double>(),
+                       fr.as<double>(), h_cost ? cs.as<double>() : nullptr, ss.as<int32_t>(), cr.as<int32_t>(),
+                       ws.ptr, SolveWorkspace::bytes(N, K), st);
+    if (rc != MINSNAP_OK) goto done;
+    TRY(cudaMemcpyAsync(h_coeffs, co.ptr, sizeof(double) * nb * K * D * N, cudaMemcpyDeviceToHost, st));
+    if (h_free_values && n_free > 0)
+      TRY(cudaMemcpyAsync(h_free_values, fr.ptr, sizeof(double) * nb * n_free * D, cudaMemcpyDeviceToHost, st));
+    if (h_cost) TRY(cudaMemcpyAsync(h_cost, cs.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+    if (h_status) TRY(cudaMemcpyAsync(h_status, ss.ptr, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+    if (h_col_of_row)
+      TRY(cudaMemcpyAsync(h_col_of_row, cr.ptr, sizeof(int32_t) * (size_t)N * K, cudaMemcpyDeviceToHost, st));
+  done:;
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  return rc;
+}
+
+int minsnap_coeffs_from_constraints_host(long B, int K, int D, int N, const uint8_t* h_fixed_mask,
+                                         const double* h_fixed_values, const double* h_free_values,
+                                         const double* h_times, double* h_coeffs) {
+  if (!shape_ok(B, K, D, N, 0) || !h_fixed_mask || !h_times || !h_coeffs) return MINSNAP_ERR_ARG;
+  int n_fixed, n_free;
+  count_mask(h_fixed_mask, N, K, &n_fixed, &n_free);
+  if ((n_fixed > 0 && !h_fixed_values) || (n_free > 0 && !h_free_values)) return MINSNAP_ERR_ARG;
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = MINSNAP_OK;
+  {
+    Scratch fv, fr, tm, co, ws;
+    const size_t nb = (size_t)B;
+    TRY(fv.alloc(sizeof(double) * nb * n_fixed * D, st));
+    TRY(fr.alloc(sizeof(double) * nb * n_free * D, st));
+    TRY(tm.alloc(sizeof(double) * nb * K, st));
+    TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
+    TRY(ws.alloc(SolveWorkspace::bytes(N, K), st));
+    if (n_fixed > 0)
+      TRY(cudaMemcpyAsync(fv.ptr, h_fixed_values, sizeof(double) * nb * n_fixed * D, cudaMemcpyHostToDevice, st));
+    if (n_free > 0)
+      TRY(cudaMemcpyAsync(fr.ptr, h_free_values, sizeof(double) * nb * n_free * D, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
+    rc = minsnap_coeffs_from_constraints(B, K, D, N, h_fixed_mask, fv.as<double>(), fr.as<double>(),
+                                         tm.as<double>(), co.as<double>(), ws.ptr, SolveWorkspace::bytes(N, K), st);
+    if (rc != MINSNAP_OK) goto done;
+    TRY(cudaMemcpyAsync(h_coeffs, co.ptr, sizeof(double) * nb * K * D * N, cudaMemcpyDeviceToHost, st));
+  done:;
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  return rc;
+}
+
+int minsnap_cost_host(long B, int K, int D, int N, int derivative, const double* h_coeffs, const double* h_times,
+                      double* h_cost) {
+  if (!shape_ok(B, K, D, N, derivative) || !h_coeffs || !h_times || !h_cost) return MINSNAP_ERR_ARG;
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = MINSNAP_OK;
+  {
+    Scratch co, tm, cs;
+    const size_t nb = (size_t)B;
+    TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
+    TRY(tm.alloc(sizeof(double) * nb * K, st));
+    TRY(cs.alloc(sizeof(double) * nb, st));
+    TRY(cudaMemcpyAsync(co.ptr, h_coeffs, sizeof(double) * nb * K * D * N, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
+    rc = minsnap_cost(B, K, D, N, derivative, co.as<double>(), tm.as<double>(), cs.as<double>(), st);
+    if (rc != MINSNAP_OK) goto done;
+    TRY(cudaMemcpyAsync(h_cost, cs.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+  done:;
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  return rc;
+}
+
+// Chunked, double-buffered pipeline: while chunk c is being solved, chunk c+1 is on its way
+// in and chunk c-1 on its way out (two streams, each with its own device buffers).
+int minsnap_solve_standard_host(long B, int K, int D, int N, int derivative, const double* h_positions,
+                                const double* h_end_derivatives, const double* h_times, double v_max,
+                                double a_max, double magic, double* h_times_out, double* h_coeffs,
+                                double* h_free_values, double* h_cost, int32_t* h_status) {
+  if (!shape_ok(B, K, D, N, derivative) || !h_positions || !h_coeffs) return MINSNAP_ERR_ARG;
+  if (!h_times && !(v_max > 0.0 && a_max > 0.0)) return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  retain_pool_memory();
+  const int h = N / 2;
+  const int n_free = (K - 1) * (h - 1);
+  const long chunk = std::min<long>(B, 16384);
+  StreamPair sp;
+  CU(sp.create());
+  int rc = MINSNAP_OK;
+  {
+    Scratch pos[2], end[2], tm[2], co[2], fr[2], cs[2], ss[2];
+    const size_t nc = (size_t)chunk;
+    int which = 0;
+    for (int s = 0; s < 2; ++s) {
+      TRY(pos[s].alloc(sizeof(double) * nc * (K + 1) * D, sp.s[s]));
+      TRY(end[s].alloc(sizeof(double) * nc * 2 * (h - 1) * D, sp.s[s]));
+      TRY(tm[s].alloc(sizeof(double) * nc * K, sp.s[s]));
+      TRY(co[s].alloc(sizeof(double) * nc * K * D * N, sp.s[s]));
+      TRY(fr[s].alloc(sizeof(double) * nc * (n_free > 0 ? n_free : 1) * D, sp.s[s]));
+      TRY(cs[s].alloc(sizeof(double) * nc, sp.s[s]));
+      TRY(ss[s].alloc(sizeof(int32_t) * nc, sp.s[s]));
+    }
+    for (long b0 = 0; b0 < B; b0 += chunk, which ^= 1) {
+      const long nb = std::min(chunk, B - b0);
+      cudaStream_t st = sp.s[which];
+      TRY(cudaMemcpyAsync(pos[which].ptr, h_positions + (size_t)b0 * (K + 1) * D,
+                          sizeof(double) * nb * (K + 1) * D, cudaMemcpyHostToDevice, st));
+      if (h_end_derivatives)
+        TRY(cudaMemcpyAsync(end[which].ptr, h_end_derivatives + (size_t)b0 * 2 * (h - 1) * D,
+                            sizeof(double) * nb * 2 * (h - 1) * D, cudaMemcpyHostToDevice, st));
+      if (h_times)
+        TRY(cudaMemcpyAsync(tm[which].ptr, h_times + (size_t)b0 * K, sizeof(double) * nb * K,
+                            cudaMemcpyHostToDevice, st));
+      rc = minsnap_solve_standard(nb, K, D, N, derivative, pos[which].as<double>(),
+                                  h_end_derivatives ? end[which].as<double>() : nullptr,
+                                  h_times ? tm[which].as<double>() : nullptr, v_max, a_max, magic,
+                                  (!h_times && h_times_out) ? tm[which].as<double>() : nullptr,
+                                  co[which].as<double>(), h_free_values ? fr[which].as<double>() : nullptr,
+                                  h_cost ? cs[which].as<double>() : nullptr,
+                                  h_status ? ss[which].as<int32_t>() : nullptr, st);
+      if (rc != MINSNAP_OK) goto done;
+      TRY(cudaMemcpyAsync(h_coeffs + (size_t)b0 * K * D * N, co[which].ptr, sizeof(double) * nb * K * D * N,
+                          cudaMemcpyDeviceToHost, st));
+      if (h_times_out) {
+        if (h_times) std::memcpy(h_times_out + (size_t)b0 * K, h_times + (size_t)b0 * K, sizeof(double) * nb * K);
+        else TRY(cudaMemcpyAsync(h_times_out + (size_t)b0 * K, tm[which].ptr, sizeof(double) * nb * K,
+                                 cudaMemcpyDeviceToHost, st));
+      }
+      if (h_free_values && n_free > 0)
+        TRY(cudaMemcpyAsync(h_free_values + (size_t)b0 * n_free * D, fr[which].ptr,
+                            sizeof(double) * nb * n_free * D, cudaMemcpyDeviceToHost, st));
+      if (h_cost) TRY(cudaMemcpyAsync(h_cost + b0, cs[which].ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+      if (h_status)
+        TRY(cudaMemcpyAsync(h_status + b0, ss[which].ptr, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+    }
+  done:;
+  }
+  for (auto st : sp.s) {
+    cudaError_t es = cudaStreamSynchronize(st);
+    if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  }
+  return rc;
+}
+
+int minsnap_sample_at_host(long B, int K, int D, int N, const double* h_coeffs, const double* h_times, int M,
+                           const double* h_t, long t_stride, int n_deriv, double* h_out, int32_t* h_segment) {
+  if (B < 0 || K < 1 || D < 1 || !minsnap::supported_n(N) || M < 0 || n_deriv < 1 || !h_coeffs || !h_times ||
+      !h_t || !h_out || (t_stride != 0 && t_stride < M))
+    return MINSNAP_ERR_ARG;
+  if (B == 0 || M == 0) return MINSNAP_OK;
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = MINSNAP_OK;
+  {
+    Scratch co, tm, tt, out, sg;
+    const size_t nb = (size_t)B;
+    const size_t n_t = t_stride == 0 ? (size_t)M : nb * (size_t)t_stride;
+    TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
+    TRY(tm.alloc(sizeof(double) * nb * K, st));
+    TRY(tt.alloc(sizeof(double) * n_t, st));
+    TRY(out.alloc(sizeof(double) * nb * M * n_deriv * D, st));
+    TRY(sg.alloc(sizeof(int32_t) * nb * M, st));
+    TRY(cudaMemcpyAsync(co.ptr, h_coeffs, sizeof(double) * nb * K * D * N, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(tt.ptr, h_t, sizeof(double) * n_t, cudaMemcpyHostToDevice, st));
+    rc = minsnap_sample_at(B, K, D, N, co.as<double>(), tm.as<double>(), M, tt.as<double>(), t_stride, n_deriv,
+                           out.as<double>(), h_segment ? sg.as<int32_t>() : nullptr, st);
+    if (rc != MINSNAP_OK) goto done;
+    TRY(cudaMemcpyAsync(h_out, out.ptr, sizeof(double) * nb * M * n_deriv * D, cudaMemcpyDeviceToHost, st));
+    if (h_segment) TRY(cudaMemcpyAsync(h_segment, sg.ptr, sizeof(int32_t) * nb * M, cudaMemcpyDeviceToHost, st));
+  done:;
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  return rc;
+}
+
+int minsnap_evaluate_range_host(int K, int D, int N, const double* h_coeffs, const double* h_times, double t_start,
+                                double t_end, double dt, int derivative, int max_samples, double* h_out,
+                                double* h_t_out, int32_t* h_count) {
+  if (K < 1 || D < 1 || !minsnap::supported_n(N) || !(dt > 0.0) || derivative < 0 || max_samples < 0 || !h_coeffs ||
+      !h_times || !h_out || !h_count)
+    return MINSNAP_ERR_ARG;
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = MINSNAP_OK;
+  {
+    Scratch co, tm, out, tt, cnt;
+    TRY(co.alloc(sizeof(double) * (size_t)K * D * N, st));
+    TRY(tm.alloc(sizeof(double) * K, st));
+    TRY(out.alloc(sizeof(double) * (size_t)max_samples * D, st));
+    TRY(tt.alloc(sizeof(double) * (size_t)max_samples, st));
+    TRY(cnt.alloc(sizeof(int32_t), st));
+    TRY(cudaMemcpyAsync(co.ptr, h_coeffs, sizeof(double) * (size_t)K * D * N, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * K, cudaMemcpyHostToDevice, st));
+    rc = minsnap_evaluate_range(1, K, D, N, co.as<double>(), tm.as<double>(), t_start, t_end, dt, derivative,
+                                max_samples, out.as<double>(), tt.as<double>(), cnt.as<int32_t>(), st);
+    if (rc != MINSNAP_OK) goto done;
+    TRY(cudaMemcpyAsync(h_count, cnt.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+    {
+      const size_t n = (size_t)std::min(*h_count, max_samples);
+      if (n > 0) {
+        TRY(cudaMemcpyAsync(h_out, out.ptr, sizeof(double) * n * D, cudaMemcpyDeviceToHost, st));
+        if (h_t_out) TRY(cudaMemcpyAsync(h_t_out, tt.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+      }
+    }
+  done:;
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  return rc;
+}
+
+int minsnap_segment_matrices_host(long n, int N, int derivative, const double* h_T, double* h_A, double* h_Ainv,
+                                  double* h_Q, double* h_H) {
+  if (n < 0 || !minsnap::supported_n(N) || derivative < 0 || derivative > N / 2 - 1 || !h_T) return MINSNAP_ERR_ARG;
+  if (n == 0) return MINSNAP_OK;
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = MINSNAP_OK;
+  {
+    Scratch T, A, Ai, Q, H;
+    const size_t mat = sizeof(double) * (size_t)n * N * N;
+    TRY(T.alloc(sizeof(double) * (size_t)n, st));
+    if (h_A) TRY(A.alloc(mat, st));
+    if (h_Ainv) TRY(Ai.alloc(mat, st));
+    if (h_Q) TRY(Q.alloc(mat, st));
+    if (h_H) TRY(H.alloc(mat, st));
+    TRY(cudaMemcpyAsync(T.ptr, h_T, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    rc = minsnap_segment_matrices(n, N, derivative, T.as<double>(), A.as<double>(), Ai.as<double>(), Q.as<double>(),
+                                  H.as<double>(), st);
+    if (rc != MINSNAP_OK) goto done;
+    if (h_A) TRY(cudaMemcpyAsync(h_A, A.ptr, mat, cudaMemcpyDeviceToHost, st));
+    if (h_Ainv) TRY(cudaMemcpyAsync(h_Ainv, Ai.ptr, mat, cudaMemcpyDeviceToHost, st));
+    if (h_Q) TRY(cudaMemcpyAsync(h_Q, Q.ptr, mat, cudaMemcpyDeviceToHost, st));
+    if (h_H) TRY(cudaMemcpyAsync(h_H, H.ptr, mat, cudaMemcpyDeviceToHost, st));
+  done:;
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  return rc;
+}
+
+int minsnap_estimate_segment_times_host(long B, int K, int D, const double* h_positions, double v_max,
+                                        double a_max, double magic, double* h_times) {
+  if (B < 0 || K < 1 || D < 1 || !h_positions || !h_times) return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = MINSNAP_OK;
+  {
+    Scratch pos, tm;
+    const size_t nb = (size_t)B;
+    TRY(pos.alloc(sizeof(double) * nb * (K + 1) * D, st));
+    TRY(tm.alloc(sizeof(double) * nb * K, st));
+    TRY(cudaMemcpyAsync(pos.ptr, h_positions, sizeof(double) * nb * (K + 1) * D, cudaMemcpyHostToDevice, st));
+    rc = minsnap_estimate_segment_times(B, K, D, pos.as<double>(), v_max, a_max, magic, tm.as<double>(), st);
+    if (rc != MINSNAP_OK) goto done;
+    TRY(cudaMemcpyAsync(h_times, tm.ptr, sizeof(double) * nb * K, cudaMemcpyDeviceToHost, st));
+  done:;
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  return rc;
+}
+#undef TRY
+
+int minsnap_fp64_peak(int repeats, double* tflops) {
+  if (!tflops || repeats < 1) return MINSNAP_ERR_ARG;
+  CU(minsnap::run_fp64_peak(repeats, tflops));
+  return MINSNAP_OK;
+}
+
+}  // extern "C"

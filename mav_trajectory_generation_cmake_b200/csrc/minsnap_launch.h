@@ -1,0 +1,91 @@
+// Internal launch interface between the C ABI (minsnap_capi.cu) and the kernel translation
+// units.  Every function enqueues work on `stream` and returns the cudaError_t of the launch.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace minsnap {
+
+// Largest dynamic shared memory a CTA may request on sm_100 (227 KB).
+constexpr size_t kMaxDynamicSmem = 227 * 1024;
+
+bool supported_n(int N);
+
+// ---- minsnap_general.cu ----------------------------------------------------------------
+cudaError_t launch_reorder(int N, int K, long n_masks, const uint8_t* d_mask, int32_t* d_col_of_row,
+                           int32_t* d_counts, cudaStream_t stream);
+cudaError_t launch_estimate_times(long B, int K, int D, const double* d_positions, double v_max,
+                                  double a_max, double magic, double* d_times, cudaStream_t stream);
+cudaError_t launch_segment_matrices(long n, int N, int derivative, const double* d_T, double* d_A,
+                                    double* d_Ainv, double* d_Q, double* d_H, cudaStream_t stream);
+
+struct GeneralSolveArgs {
+  long B;
+  int K, D, N, derivative, n_fixed, n_free;
+  int fixed_div = 1;            // problem b uses fixed-value record b / fixed_div
+  const int32_t* d_col_of_row;  // [N*K]
+  const double* d_fixed_values; // [B][n_fixed][D]
+  const double* d_free_in;      // [B][n_free][D]; only for coefficient recovery
+  const double* d_times;        // [B][K]
+  double* d_coeffs;             // [B][K][D][N] (optional for cost-only runs)
+  double* d_free_out;           // optional
+  double* d_cost;               // optional
+  int32_t* d_status;            // optional
+};
+// Returns cudaErrorInvalidConfiguration when one problem does not fit shared memory.
+cudaError_t launch_solve_general(const GeneralSolveArgs& a, cudaStream_t stream);
+cudaError_t launch_coeffs_from_constraints(const GeneralSolveArgs& a, cudaStream_t stream);
+cudaError_t launch_cost(long B, int K, int D, int N, int derivative, const double* d_coeffs,
+                        const double* d_times, double* d_cost, cudaStream_t stream);
+
+// ---- minsnap_standard.cu ---------------------------------------------------------------
+struct StandardSolveArgs {
+  long B;
+  int K, D, N, derivative;
+  const double* d_positions;       // [B][K+1][D]
+  const double* d_end_derivatives; // [B][2][h-1][D] or NULL
+  const double* d_times;           // [B][K] or NULL
+  double v_max, a_max, magic;
+  double* d_times_out;             // optional
+  double* d_coeffs;                // [B][K][D][N]
+  double* d_free_out;              // optional [B][n_free][D]
+  double* d_cost;                  // optional
+  int32_t* d_status;               // optional
+};
+bool standard_supported(int K, int D, int N, int derivative);
+cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t stream);
+
+struct SweepArgs {
+  long B;
+  int S, K, D, N, derivative;
+  const double* d_positions;
+  const double* d_end_derivatives;
+  const double* d_times; // [B][S][K]
+  double* d_cost;        // [B][S]
+  int32_t* d_status;     // optional [B][S]
+};
+cudaError_t launch_cost_sweep(const SweepArgs& a, cudaStream_t stream);
+
+// ---- minsnap_sample.cu -----------------------------------------------------------------
+struct SampleArgs {
+  long B;
+  int K, D, N, M, n_deriv;
+  const double* d_coeffs;
+  const double* d_times;
+  const double* d_t;   // NULL => uniform grid
+  long t_stride;       // 0 => shared row
+  double* d_out;       // [B][M][n_deriv][D]
+  double* d_t_out;     // optional [B][M]
+  int32_t* d_segment;  // optional [B][M]
+};
+cudaError_t launch_sample(const SampleArgs& a, cudaStream_t stream);
+cudaError_t launch_evaluate_range(long B, int K, int D, int N, const double* d_coeffs,
+                                  const double* d_times, double t_start, double t_end, double dt,
+                                  int derivative, int max_samples, double* d_out, double* d_t_out,
+                                  int32_t* d_count, cudaStream_t stream);
+
+// ---- minsnap_peak.cu -------------------------------------------------------------------
+cudaError_t run_fp64_peak(int repeats, double* tflops);
+
+}  // namespace minsnap

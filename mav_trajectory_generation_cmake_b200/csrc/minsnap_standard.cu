@@ -1,0 +1,124 @@
+// Standard-mask path: the constraint structure createRandomVertices produces (ref:
+// src/vertex.cpp:59,71-76) -- end vertices fix derivatives 0..h-1, interior vertices fix
+// position only.  n_fixed = K + 2h - 1, n_free = (K-1)(h-1).
+//
+// Two routes, both on the GPU:
+//   * fast route (minsnap_standard_fast.cuh): N = 10, snap, a thread pair per trajectory;
+//   * generic route: pack the inputs into the general layout and run the general kernels
+//     (any N, K, D, derivative the general path supports).
+#include "minsnap_device.cuh"
+#include "minsnap_launch.h"
+#include "minsnap_standard_fast.cuh"
+
+namespace minsnap {
+
+// ---- generic route ------------------------------------------------------------------------
+__global__ void standard_mask_kernel(int K, int h, uint8_t* __restrict__ mask) {
+  const int nc = (K + 1) * h;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nc; e += gridDim.x * blockDim.x) {
+    const int v = e / h, c = e - v * h;
+    mask[e] = (c == 0 || v == 0 || v == K) ? 1 : 0;
+  }
+}
+
+// fixed_values[b][col][dim] in the reference's column order: vertex 0 (derivatives 0..h-1),
+// vertices 1..K-1 (position), vertex K (derivatives 0..h-1).
+__global__ void pack_standard_kernel(long B, int K, int D, int h, const double* __restrict__ positions,
+                                     const double* __restrict__ end_derivatives, double* __restrict__ fixed_values) {
+  const int n_fixed = K + 2 * h - 1;
+  const long total = B * (long)n_fixed * D;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int dim = (int)(e % D);
+    const int col = (int)((e / D) % n_fixed);
+    const long b = e / ((long)D * n_fixed);
+    int v, c;
+    if (col < h) { v = 0; c = col; }
+    else if (col < h + K - 1) { v = col - h + 1; c = 0; }
+    else { v = K; c = col - (h + K - 1); }
+    double val;
+    if (c == 0) val = positions[(b * (K + 1) + v) * D + dim];
+    else val = end_derivatives ? end_derivatives[((b * 2 + (v == K)) * (h - 1) + (c - 1)) * D + dim] : 0.0;
+    fixed_values[e] = val;
+  }
+}
+
+struct AsyncBuffer {
+  void* ptr = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaError_t alloc(size_t bytes, cudaStream_t s) {
+    stream = s;
+    return cudaMallocAsync(&ptr, bytes ? bytes : 16, s);
+  }
+  ~AsyncBuffer() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+  }
+};
+
+static cudaError_t generic_route(long B, int S, int K, int D, int N, int derivative, const double* d_positions,
+                                 const double* d_end_derivatives, const double* d_times, double* d_coeffs,
+                                 double* d_free_out, double* d_cost, int32_t* d_status, cudaStream_t stream) {
+  const int h = N / 2;
+  const int n_fixed = K + 2 * h - 1;
+  const int n_free = (K - 1) * (h - 1);
+  AsyncBuffer mask, col, counts, fixed;
+  cudaError_t e;
+  if ((e = mask.alloc((size_t)(K + 1) * h, stream)) != cudaSuccess) return e;
+  if ((e = col.alloc(sizeof(int32_t) * (size_t)N * K, stream)) != cudaSuccess) return e;
+  if ((e = counts.alloc(sizeof(int32_t) * 2, stream)) != cudaSuccess) return e;
+  if ((e = fixed.alloc(sizeof(double) * (size_t)B * n_fixed * D, stream)) != cudaSuccess) return e;
+  standard_mask_kernel<<<((K + 1) * h + 255) / 256, 256, 0, stream>>>(K, h, static_cast<uint8_t*>(mask.ptr));
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = launch_reorder(N, K, 1, static_cast<uint8_t*>(mask.ptr), static_cast<int32_t*>(col.ptr),
+                          static_cast<int32_t*>(counts.ptr), stream)) != cudaSuccess)
+    return e;
+  {
+    const long total = B * (long)n_fixed * D;
+    long grid = (total + 255) / 256;
+    if (grid > 148L * 16) grid = 148L * 16;
+    pack_standard_kernel<<<(int)grid, 256, 0, stream>>>(B, K, D, h, d_positions, d_end_derivatives,
+                                                        static_cast<double*>(fixed.ptr));
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  GeneralSolveArgs g;
+  g.B = B * S; g.K = K; g.D = D; g.N = N; g.derivative = derivative; g.n_fixed = n_fixed; g.n_free = n_free;
+  g.fixed_div = S;
+  g.d_col_of_row = static_cast<int32_t*>(col.ptr);
+  g.d_fixed_values = static_cast<double*>(fixed.ptr);
+  g.d_free_in = nullptr;
+  g.d_times = d_times; g.d_coeffs = d_coeffs; g.d_free_out = d_free_out; g.d_cost = d_cost; g.d_status = d_status;
+  return launch_solve_general(g, stream);
+}
+
+bool standard_supported(int K, int D, int N, int derivative) { return fast::supported(K, D, N, derivative); }
+
+cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t stream) {
+  if (a.B == 0) return cudaSuccess;
+  AsyncBuffer times_scratch;
+  const double* times = a.d_times;
+  cudaError_t e;
+  const bool fast_ok = fast::supported(a.K, a.D, a.N, a.derivative);
+  if (!times && !fast_ok) {
+    // the generic route needs the times in memory; the fast kernel computes them in-register
+    double* dst = a.d_times_out;
+    if (!dst) {
+      if ((e = times_scratch.alloc(sizeof(double) * (size_t)a.B * a.K, stream)) != cudaSuccess) return e;
+      dst = static_cast<double*>(times_scratch.ptr);
+    }
+    if ((e = launch_estimate_times(a.B, a.K, a.D, a.d_positions, a.v_max, a.a_max, a.magic, dst, stream)) !=
+        cudaSuccess)
+      return e;
+    times = dst;
+  }
+  if (fast_ok) return fast::launch(a, stream);
+  return generic_route(a.B, 1, a.K, a.D, a.N, a.derivative, a.d_positions, a.d_end_derivatives, times, a.d_coeffs,
+                       a.d_free_out, a.d_cost, a.d_status, stream);
+}
+
+cudaError_t launch_cost_sweep(const SweepArgs& a, cudaStream_t stream) {
+  if (a.B == 0) return cudaSuccess;
+  if (fast::sweep_supported(a.K, a.D, a.N, a.derivative)) return fast::launch_sweep(a, stream);
+  return generic_route(a.B, a.S, a.K, a.D, a.N, a.derivative, a.d_positions, a.d_end_derivatives, a.d_times, nullptr,
+                       nullptr, a.d_cost, a.d_status, stream);
+}
+
+}  // namespace minsnap
