@@ -78,9 +78,13 @@ def test_segment_matrices(ms, oracle, oracle_ld, torch_cuda):
     for i, t in enumerate(T):
         A = oracle.mapping_matrix(N, t)
         assert np.abs(out["A"][i] - A).max() <= 1e-14 * np.abs(A).max()
-        # T:194-204: block inverse vs the full inverse, 1e-10 absolute (for t >= 1 as in the reference)
+        # T:194-204 compares the block inverse with Eigen's A.inverse() at 1e-10 absolute; the
+        # oracle's own partial-pivot full inverse is itself only good to ~3e-10 at t = 1, so the
+        # bar against it is 1e-9 and the tight check is the extended-precision one below.
         if t >= 1.0:
-            assert np.abs(out["Ainv"][i] - oracle.dense_inverse(A)).max() < 1e-10
+            assert np.abs(out["Ainv"][i] - oracle.dense_inverse(A)).max() < 1e-9
+            Ai_ld_full = oracle_ld.dense_inverse(oracle_ld.mapping_matrix(N, t)).astype(np.float64)
+            assert np.abs(out["Ainv"][i] - Ai_ld_full).max() < 1e-10
         Ai_ld = oracle_ld.invert_mapping_matrix(oracle_ld.mapping_matrix(N, t)).astype(np.float64)
         assert np.abs(out["Ainv"][i] - Ai_ld).max() <= 1e-13 * np.abs(Ai_ld).max()
         Q = oracle.cost_matrix(N, SNAP, t)
@@ -100,22 +104,39 @@ def run_general(ms, torch, mask, values, times, N_=N, derivative=SNAP):
     return ms.solve(mask, dev(torch, fixed), dev(torch, times), N=N_, derivative=derivative)
 
 
-def compare_with_oracle(oracle, out, mask, values, times, N_=N, derivative=SNAP, coeff_tol=COEFF_TOL):
+def compare_with_oracle(oracle, out, mask, values, times, N_=N, derivative=SNAP, coeff_tol=COEFF_TOL, truth=None):
+    """GPU vs the f64 oracle at the north-star tolerances.  With `truth` (the long-double build
+    of the oracle) the GPU result must be within tolerance of the truth, and the allowance
+    against the f64 oracle is widened by that oracle's own distance from the truth -- needed
+    only off the north-star shape (exotic masks, N = 12, low derivative orders), where the
+    reference-order f64 arithmetic (Ainv^T Q Ainv, cond(A) up to 1e12) is itself ~1e-8 off."""
     ref = oracle_solve_batch(oracle, mask, values, times, N_, derivative)
     assert (ref["status"] == 0).all()
     assert (out["status"].cpu().numpy() == 0).all()
     col_ref, nf, npf = oracle.reorder(N_, mask.shape[0] - 1, mask)
     assert np.array_equal(out["col_of_row"].cpu().numpy(), col_ref)
     coeffs = out["coeffs"].cpu().numpy()
-    assert coeff_rel_err(coeffs, ref["coeffs"]) <= coeff_tol
+    slack = 0.0
+    want_free = np.transpose(ref["d_free"], (0, 2, 1))
+    free_slack = 0.0
+    if truth is not None:
+        ref_t = oracle_solve_batch(truth, mask, values, times, N_, derivative)
+        assert coeff_rel_err(coeffs, ref_t["coeffs"]) <= coeff_tol
+        slack = 2.0 * coeff_rel_err(ref["coeffs"], ref_t["coeffs"])
+        if npf > 0:
+            truth_free = np.transpose(ref_t["d_free"], (0, 2, 1))
+            scale_t = np.abs(truth_free).max(axis=(1, 2), keepdims=True)
+            free = out["free_values"].cpu().numpy()
+            assert (np.abs(free - truth_free) / scale_t).max() <= 1e-8
+            free_slack = 2.0 * (np.abs(want_free - truth_free) / scale_t).max()
+    assert coeff_rel_err(coeffs, ref["coeffs"]) <= coeff_tol + slack
     if npf > 0:
         free = out["free_values"].cpu().numpy()              # [B][n_free][D]
-        want = np.transpose(ref["d_free"], (0, 2, 1))
-        scale = np.abs(want).max(axis=(1, 2), keepdims=True)
-        assert (np.abs(free - want) / scale).max() <= 1e-8
+        scale = np.abs(want_free).max(axis=(1, 2), keepdims=True)
+        assert (np.abs(free - want_free) / scale).max() <= 1e-8 + free_slack
     if out["cost"] is not None:
         cost = out["cost"].cpu().numpy()
-        assert np.abs(cost / ref["cost"] - 1.0).max() <= COST_TOL
+        assert np.abs(cost / ref["cost"] - 1.0).max() <= COST_TOL + slack
     return coeffs, ref
 
 
@@ -177,7 +198,7 @@ def test_general_solve_constraint_packing(ms, oracle, torch_cuda):
                 assert np.abs(A[b, s] @ p - d_seg).max() < 1e-6
 
 
-def test_general_solve_random_masks_and_values(ms, oracle, torch_cuda):
+def test_general_solve_random_masks_and_values(ms, oracle, oracle_ld, torch_cuda):
     """Arbitrary fixed/free patterns (position always fixed so the QP is strictly convex) with
     non-zero derivative constraints."""
     rng = np.random.default_rng(3)
@@ -190,19 +211,19 @@ def test_general_solve_random_masks_and_values(ms, oracle, torch_cuda):
             values = batch_values(pos)
             values[:, :, 1:, :] = rng.normal(size=values[:, :, 1:, :].shape)
             out = run_general(ms, torch_cuda, mask, values, times)
-            coeffs, _ = compare_with_oracle(oracle, out, mask, values, times)
+            coeffs, _ = compare_with_oracle(oracle, out, mask, values, times, truth=oracle_ld)
             assert check_path(coeffs[0], times[0], mask, values[0], oracle) < 1e-6
 
 
 @pytest.mark.parametrize("N_,derivative", [(10, 3), (10, 2), (8, 3), (6, 2), (12, 5), (4, 1)])
-def test_general_solve_other_orders(ms, oracle, torch_cuda, N_, derivative):
+def test_general_solve_other_orders(ms, oracle, oracle_ld, torch_cuda, N_, derivative):
     K, B = 6, 16
     h = N_ // 2
     pos, times = random_batch(oracle, B, K, 3, seed=77)
     mask = standard_mask(K, N_)
     values = batch_values(pos, N_)
     out = run_general(ms, torch_cuda, mask, values, times, N_, derivative)
-    compare_with_oracle(oracle, out, mask, values, times, N_, derivative)
+    compare_with_oracle(oracle, out, mask, values, times, N_, derivative, truth=oracle_ld)
     assert out["coeffs"].shape == (B, K, 3, N_) and h * (K + 1) == mask.size
 
 
@@ -362,7 +383,9 @@ def test_coeffs_from_constraints_and_cost(ms, oracle, torch_cuda):
         assert coeff_rel_err(got[b], want) <= COEFF_TOL
     cost = ms.cost(dev(torch, got), dev(torch, times)).cpu().numpy()
     want_cost = np.array([float(oracle.compute_cost(N, K, 3, SNAP, got[b], times[b])) for b in range(B)])
-    assert np.abs(cost / want_cost - 1.0).max() <= 1e-12
+    # random (non-optimal) free derivatives make c^T Q c a sum of large cancelling terms: the two
+    # summation orders agree to ~1e-10; the north-star bar for cost is 1e-8 relative
+    assert np.abs(cost / want_cost - 1.0).max() <= 1e-9
     assert np.array_equal(cost, ms.cost_host(got, times))
 
 
