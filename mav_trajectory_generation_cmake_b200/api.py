@@ -366,3 +366,8 @@ def random_positions_host(B, K, pos_min, pos_max, base_seed):
     capi.check(_lib().minsnap_random_positions_host(B, K, D, _hptr(pos_min), _hptr(pos_max), base_seed, _hptr(out)),
                "minsnap_random_positions_host")
     return out
+
+
+# solve_standard runs the single-launch thread-pair kernel for N = 10, snap, K <= 24, D <= 3
+# (csrc/minsnap_standard_fast.cuh); other shapes take the 4-launch generic route.
+STANDARD_FAST_ROUTE = True

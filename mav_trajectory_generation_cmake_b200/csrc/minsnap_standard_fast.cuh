@@ -1,5 +1,31 @@
-// Fast route for the standard mask (N = 10, snap): placeholder until the thread-pair kernel
-// lands; every shape currently takes the generic route.
+// Fast route for the standard mask (N = 10, snap): a THREAD PAIR per trajectory.
+//
+// Algebra (notes A and B).  Unknowns are the free derivatives k = 1..4 at
+// the interior vertices v = 1..K-1 (x_v in R^4 per dimension); R_pp is symmetric block
+// tridiagonal with 4x4 blocks:
+//     SE_{v-1}^T x_{v-1} + D_v x_v + SE_v x_{v+1} = b_v ,  x_0, x_K known (end derivatives)
+//     D_v  = EE_{v-1} + SS_v          SS/EE/SE = start-free / end-free blocks of H_T
+//     b_v  = -(ge_{v-1} dp_{v-1} + gs_v dp_v)   dp_i = p_{i+1} - p_i  (H annihilates constants,
+//                                               so H[:,start pos] = -H[:,end pos])
+// with H_T[r][s] = H1[r][s] T^(k_r + k_s - 7) taken from the exact unit-time table.
+//
+// Parallel scheme ("burn at both ends"): lane 2q eliminates the chain top-down from vertex 1,
+// lane 2q+1 bottom-up from vertex K-1; they meet at the middle block, exchange their Schur
+// contributions with one shuffle, solve the middle block (both lanes, identical arithmetic),
+// then back-substitute outwards.  Time reversal maps derivative k to (-1)^k times itself and
+// leaves the unit table invariant, so the bottom-up lane runs the SAME program on reversed
+// inputs ("local coordinates") and flips the signs of odd derivatives when it leaves them.
+// Each lane recovers the coefficients (ref: updateSegmentsFromCompactConstraints,
+// LIN.i:252-273) of its half of the segments as soon as both end-point derivative vectors of a
+// segment are known, through  c_i = T^-i sum_r A1inv[i][r] T^(k_r) d_r .
+//
+// Per block, per lane:  S = L D L^T (no square roots), Z = S^-1 SE, w = S^-1 g are kept in
+// shared memory ([slot][lane], stride 33 doubles: conflict-free both per-lane and transposed);
+// Schur update S' = D' - SE^T Z, g' = b' - SE^T w;  back substitution x = w - Z x_next.
+//
+// HBM traffic is the algorithmic minimum: positions and times are read once with coalesced
+// warp-wide loads into shared memory, coefficients are transposed through shared memory and
+// written as full 16-byte-per-lane coalesced stores.
 #pragma once
 #include "minsnap_device.cuh"
 #include "minsnap_launch.h"
@@ -7,10 +33,689 @@
 namespace minsnap {
 namespace fast {
 
-inline bool supported(int, int, int, int) { return false; }
-inline bool sweep_supported(int, int, int, int) { return false; }
-inline cudaError_t launch(const StandardSolveArgs&, cudaStream_t) { return cudaErrorNotSupported; }
-inline cudaError_t launch_sweep(const SweepArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+constexpr int kN = 10;          // coefficients per polynomial
+constexpr int kF = 4;           // free derivatives per interior vertex (k = 1..4)
+constexpr int kPairsPerWarp = 16;
+constexpr int kSlotStride = 33; // doubles between consecutive slots of one lane
+constexpr int kBlockSlots = kF * kF;  // Z of one block
+constexpr int kMaxK = 24;
+
+#define H1T(r, s) (minsnap_tables::kH1_N10_d4[(r) * 10 + (s)])
+#define A1T(i, r) (minsnap_tables::kA1inv_N10[(i) * 10 + (r)])
+
+// 1/x for a positive normal double: hardware seed (~20 bits) + two Newton steps.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// P[m] = T^(m-7) for m = 1..8 (P[0] unused).
+struct TimePowers {
+  double P[9];
+  __device__ __forceinline__ void set(double T) {
+    const double i1 = fast_rcp(T);
+    const double i2 = i1 * i1;
+    const double i3 = i2 * i1;
+    const double i4 = i2 * i2;
+    P[8] = T; P[7] = 1.0; P[6] = i1; P[5] = i2; P[4] = i3; P[3] = i4; P[2] = i4 * i1; P[1] = i3 * i3;
+    P[0] = 0.0;
+  }
+};
+
+// Lower triangle of a symmetric 4x4, packed row-wise: (0,0) (1,0) (1,1) (2,0) (2,1) (2,2) (3,0)...
+__device__ __forceinline__ constexpr int tri(int a, int b) { return a * (a + 1) / 2 + b; }
+
+// S = L D L^T.  On return l[tri(a,b)] (a > b) holds L, inv[a] = 1/D_a.  Returns false if a
+// pivot is not positive.
+__device__ __forceinline__ bool ldlt4(const double (&s)[10], double (&l)[10], double (&inv)[4]) {
+  bool ok = true;
+  const double d0 = s[tri(0, 0)];
+  ok &= d0 > 0.0;
+  inv[0] = fast_rcp(d0);
+  l[tri(1, 0)] = s[tri(1, 0)] * inv[0];
+  l[tri(2, 0)] = s[tri(2, 0)] * inv[0];
+  l[tri(3, 0)] = s[tri(3, 0)] * inv[0];
+  const double d1 = fma(-l[tri(1, 0)], s[tri(1, 0)], s[tri(1, 1)]);
+  ok &= d1 > 0.0;
+  inv[1] = fast_rcp(d1);
+  const double t21 = fma(-l[tri(2, 0)], s[tri(1, 0)], s[tri(2, 1)]);
+  const double t31 = fma(-l[tri(3, 0)], s[tri(1, 0)], s[tri(3, 1)]);
+  l[tri(2, 1)] = t21 * inv[1];
+  l[tri(3, 1)] = t31 * inv[1];
+  const double d2 = fma(-l[tri(2, 1)], t21, fma(-l[tri(2, 0)], s[tri(2, 0)], s[tri(2, 2)]));
+  ok &= d2 > 0.0;
+  inv[2] = fast_rcp(d2);
+  const double t32 = fma(-l[tri(3, 1)], t21, fma(-l[tri(3, 0)], s[tri(2, 0)], s[tri(3, 2)]));
+  l[tri(3, 2)] = t32 * inv[2];
+  const double d3 = fma(-l[tri(3, 2)], t32, fma(-l[tri(3, 1)], t31, fma(-l[tri(3, 0)], s[tri(3, 0)], s[tri(3, 3)])));
+  ok &= d3 > 0.0;
+  inv[3] = fast_rcp(d3);
+  return ok;
+}
+
+// y <- S^-1 y with the factor above.
+__device__ __forceinline__ void ldlt4_solve(const double (&l)[10], const double (&inv)[4], double (&y)[4]) {
+  y[1] = fma(-l[tri(1, 0)], y[0], y[1]);
+  y[2] = fma(-l[tri(2, 1)], y[1], fma(-l[tri(2, 0)], y[0], y[2]));
+  y[3] = fma(-l[tri(3, 2)], y[2], fma(-l[tri(3, 1)], y[1], fma(-l[tri(3, 0)], y[0], y[3])));
+  y[0] *= inv[0]; y[1] *= inv[1]; y[2] *= inv[2]; y[3] *= inv[3];
+  y[2] = fma(-l[tri(3, 2)], y[3], y[2]);
+  y[1] = fma(-l[tri(3, 1)], y[3], fma(-l[tri(2, 1)], y[2], y[1]));
+  y[0] = fma(-l[tri(3, 0)], y[3], fma(-l[tri(2, 0)], y[2], fma(-l[tri(1, 0)], y[1], y[0])));
+}
+
+// Diagonal block D = EE(T_prev) + SS(T_next) in the coordinates of the lane (lower triangle).
+__device__ __forceinline__ void diag_block(const TimePowers& prev, const TimePowers& next, double (&s)[10]) {
+#pragma unroll
+  for (int a = 0; a < kF; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      const int m = a + b + 2;  // derivative orders (a+1) + (b+1)
+      const double mix = ((a + b) & 1) ? next.P[m] - prev.P[m] : next.P[m] + prev.P[m];
+      s[tri(a, b)] = H1T(a + 1, b + 1) * mix;
+    }
+}
+
+// Coupling block SE(T)[a][b] = H1[a+1][6+b] T^(a+b+2-7).
+__device__ __forceinline__ void coupling_block(const TimePowers& t, double (&e)[kF][kF]) {
+#pragma unroll
+  for (int a = 0; a < kF; ++a)
+#pragma unroll
+    for (int b = 0; b < kF; ++b) e[a][b] = H1T(a + 1, 6 + b) * t.P[a + b + 2];
+}
+
+struct FastParams {
+  long B;
+  int K;
+  const double* positions;
+  const double* end_derivatives;
+  const double* times;
+  double v_max, a_max, magic;
+  double* times_out;
+  double* coeffs;
+  double* free_out;
+  double* cost;
+  int32_t* status;
+  int sweep_S;  // > 0: cost-only time sweep, times is [B][S][K]
+};
+
+template <int D>
+__host__ __device__ inline int lane_slots(int K) {
+  const int mA = (K - 1) / 2;
+  const int a = (kBlockSlots + kF * D) * mA;
+  const int b = kF * D * mA + D * kN;
+  return a > b ? a : b;
+}
+
+template <int D>
+__host__ __device__ inline size_t warp_smem_doubles(int K) {
+  // [slots][33] + positions [16][(K+1) D | 1] + times [16][K | 1]  (odd strides: conflict-free)
+  const int ps = ((K + 1) * D) | 1;
+  const int ts = K | 1;
+  return (size_t)lane_slots<D>(K) * kSlotStride + (size_t)kPairsPerWarp * (ps + ts);
+}
+
+// ------------------------------------------------------------------------------------------
+// The kernel.  kCoeffs: recover and store coefficients; cost is computed when p.cost != NULL.
+// ------------------------------------------------------------------------------------------
+template <int D, bool kCoeffs>
+__global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int K = p.K;
+  const int pos_stride = ((K + 1) * D) | 1;
+  const int time_stride = K | 1;
+  double* wbase = smem + (size_t)warp * warp_smem_doubles<D>(K);
+  double* slots = wbase;                                                 // [n_slots][33]
+  double* pos_s = slots + (size_t)lane_slots<D>(K) * kSlotStride;        // [16][pos_stride]
+  double* time_s = pos_s + kPairsPerWarp * pos_stride;                   // [16][time_stride]
+
+  const int side = lane & 1;   // 0: top-down lane, 1: bottom-up lane
+  const int q = lane >> 1;     // pair index within the warp
+  const int nb = K - 1;        // unknown blocks
+  const int mA = nb / 2;       // blocks eliminated top-down; the middle block is vertex mA + 1
+  const int nB = nb - mA - 1;  // blocks eliminated bottom-up
+  const int my_n = side ? nB : mA;
+  const int x_off = 0;                   // slot of w/x of block j (1-based): x_off + (j-1) * kF * D
+  const int z_off = kF * D * mA;         // slot of Z of block j: z_off + (j-1) * 16; also coefficient staging
+  const double flip[kF] = {side ? -1.0 : 1.0, 1.0, side ? -1.0 : 1.0, 1.0};  // (-1)^k, k = 1..4, for lane 1
+
+  const long n_problems = p.sweep_S > 0 ? p.B * p.sweep_S : p.B;
+  const long pairs_per_cta = (long)warps_per_cta * kPairsPerWarp;
+
+  for (long base = (long)blockIdx.x * pairs_per_cta + (long)warp * kPairsPerWarp; base < n_problems;
+       base += (long)gridDim.x * pairs_per_cta) {
+    const int n_here = (int)min((long)kPairsPerWarp, n_problems - base);
+    const long prob = base + q;          // problem of this pair
+    const bool active = q < n_here;
+    __syncwarp();
+    // ---- stage inputs: coalesced global reads, odd-stride shared layout -------------------
+    {
+      const int per_pos = (K + 1) * D;
+      if (p.sweep_S > 0) {
+        for (int e = lane; e < n_here * per_pos; e += kWarp) {
+          const int r = e / per_pos, o = e - r * per_pos;
+          pos_s[r * pos_stride + o] = p.positions[((base + r) / p.sweep_S) * per_pos + o];
+        }
+      } else {
+        const double* src = p.positions + base * per_pos;
+        for (int e = lane; e < n_here * per_pos; e += kWarp) {
+          const int r = e / per_pos, o = e - r * per_pos;
+          pos_s[r * pos_stride + o] = src[e];
+        }
+      }
+      if (p.times) {
+        const double* tsrc = p.times + base * K;
+        for (int e = lane; e < n_here * K; e += kWarp) {
+          const int r = e / K, o = e - r * K;
+          time_s[r * time_stride + o] = tsrc[e];
+        }
+      }
+      __syncwarp();
+      if (!p.times) {
+        // ref estimateSegmentTimes (src/vertex.cpp:162-178), same expression as minsnap_estimate_segment_times
+        for (int e = lane; e < n_here * K; e += kWarp) {
+          const int r = e / K, o = e - r * K;
+          const double* p0 = pos_s + r * pos_stride + o * D;
+          double s2 = 0.0;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const double diff = p0[D + d] - p0[d];
+            s2 += diff * diff;
+          }
+          const double distance = sqrt(s2);
+          const double T = distance / p.v_max * 2 * (1.0 + p.magic * p.v_max / p.a_max * exp(-distance / p.v_max * 2));
+          time_s[r * time_stride + o] = T;
+          if (p.times_out) p.times_out[(base + r) * K + o] = T;
+        }
+        __syncwarp();
+      }
+    }
+
+    const double* my_pos = pos_s + q * pos_stride;
+    const double* my_time = time_s + q * time_stride;
+    // local chain: vertex j <-> actual vertex (side ? K - j : j); segment j (between local
+    // vertices j and j+1) <-> actual segment (side ? K-1-j : j)
+    auto local_T = [&](int j) { return my_time[side ? K - 1 - j : j]; };
+    auto local_p = [&](int j, int d) { return my_pos[(side ? K - j : j) * D + d]; };
+
+    int status = 0;
+    double* my_slots = slots + lane;     // slot s of this lane: my_slots[s * 33]
+
+    // boundary derivatives of the local chain (vertex 0 of the lane), in local coordinates
+    double bd[kF][D];
+#pragma unroll
+    for (int a = 0; a < kF; ++a)
+#pragma unroll
+      for (int d = 0; d < D; ++d) bd[a][d] = 0.0;
+    if (p.end_derivatives && active) {
+      const long rec = p.sweep_S > 0 ? prob / p.sweep_S : prob;
+      const double* src = p.end_derivatives + (rec * 2 + side) * (kF * D);
+#pragma unroll
+      for (int a = 0; a < kF; ++a)
+#pragma unroll
+        for (int d = 0; d < D; ++d) bd[a][d] = flip[a] * src[a * D + d];
+    }
+
+    double xm[kF][D];   // middle block solution, local coordinates
+    TimePowers tp_prev, tp_next;
+    double dp_prev[D], dp_next[D];
+    if (nb > 0) {
+      // ---- forward sweep ------------------------------------------------------------------
+      double S[10], g[kF][D];
+      tp_prev.set(local_T(0));
+      tp_next.set(local_T(1));
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        dp_prev[d] = local_p(1, d) - local_p(0, d);
+        dp_next[d] = K >= 2 ? local_p(2, d) - local_p(1, d) : 0.0;
+      }
+      // block 1: D_1 and b_1 (with the known boundary derivatives moved to the right-hand side)
+      auto rhs_block = [&](const TimePowers& tprev, const TimePowers& tnext, const double (&dprev)[D],
+                           const double (&dnext)[D], double (&out)[kF][D]) {
+#pragma unroll
+        for (int a = 0; a < kF; ++a) {
+          const double ce = H1T(6 + a, 5) * tprev.P[a + 1];   // ge: end-free row of the previous segment
+          const double cs = H1T(1 + a, 5) * tnext.P[a + 1];   // gs: start-free row of the next segment
+#pragma unroll
+          for (int d = 0; d < D; ++d) out[a][d] = -fma(ce, dprev[d], cs * dnext[d]);
+        }
+      };
+      diag_block(tp_prev, tp_next, S);
+      rhs_block(tp_prev, tp_next, dp_prev, dp_next, g);
+      if (p.end_derivatives) {
+        double E0[kF][kF];
+        coupling_block(tp_prev, E0);
+#pragma unroll
+        for (int b = 0; b < kF; ++b)
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            double acc = g[b][d];
+#pragma unroll
+            for (int a = 0; a < kF; ++a) acc = fma(-E0[a][b], bd[a][d], acc);
+            g[b][d] = acc;
+          }
+      }
+
+      double C[10], c[kF][D];   // Schur contribution of this lane to the middle block
+#pragma unroll
+      for (int i = 0; i < 10; ++i) C[i] = 0.0;
+#pragma unroll
+      for (int a = 0; a < kF; ++a)
+#pragma unroll
+        for (int d = 0; d < D; ++d) c[a][d] = 0.0;
+
+      for (int j = 1; j <= mA; ++j) {
+        if (j <= my_n) {
+          // here: tp_prev = segment j-1, tp_next = segment j, S/g = reduced block j
+          double L[10], inv[4];
+          if (!ldlt4(S, L, inv)) status |= 1;
+          double E[kF][kF];
+          coupling_block(tp_next, E);
+          double Z[kF][kF];
+#pragma unroll
+          for (int b = 0; b < kF; ++b) {
+            double col[4] = {E[0][b], E[1][b], E[2][b], E[3][b]};
+            ldlt4_solve(L, inv, col);
+#pragma unroll
+            for (int a = 0; a < kF; ++a) {
+              Z[a][b] = col[a];
+              my_slots[(z_off + (j - 1) * kBlockSlots + a * kF + b) * kSlotStride] = col[a];
+            }
+          }
+          double w[kF][D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            double col[4] = {g[0][d], g[1][d], g[2][d], g[3][d]};
+            ldlt4_solve(L, inv, col);
+#pragma unroll
+            for (int a = 0; a < kF; ++a) {
+              w[a][d] = col[a];
+              my_slots[(x_off + (j - 1) * kF * D + a * D + d) * kSlotStride] = col[a];
+            }
+          }
+          // advance to block j+1 (or, at the last block of the lane, leave the Schur terms)
+          tp_prev = tp_next;
+#pragma unroll
+          for (int d = 0; d < D; ++d) dp_prev[d] = dp_next[d];
+          if (j < my_n) {
+            tp_next.set(local_T(j + 1));
+#pragma unroll
+            for (int d = 0; d < D; ++d) dp_next[d] = local_p(j + 2, d) - local_p(j + 1, d);
+            diag_block(tp_prev, tp_next, S);
+            rhs_block(tp_prev, tp_next, dp_prev, dp_next, g);
+#pragma unroll
+            for (int a = 0; a < kF; ++a)
+#pragma unroll
+              for (int b = 0; b <= a; ++b) {
+                double acc = S[tri(a, b)];
+#pragma unroll
+                for (int r = 0; r < kF; ++r) acc = fma(-E[r][a], Z[r][b], acc);
+                S[tri(a, b)] = acc;
+              }
+#pragma unroll
+            for (int a = 0; a < kF; ++a)
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                double acc = g[a][d];
+#pragma unroll
+                for (int r = 0; r < kF; ++r) acc = fma(-E[r][a], w[r][d], acc);
+                g[a][d] = acc;
+              }
+          } else {
+#pragma unroll
+            for (int a = 0; a < kF; ++a)
+#pragma unroll
+              for (int b = 0; b <= a; ++b) {
+                double acc = 0.0;
+#pragma unroll
+                for (int r = 0; r < kF; ++r) acc = fma(E[r][a], Z[r][b], acc);
+                C[tri(a, b)] = acc;
+              }
+#pragma unroll
+            for (int a = 0; a < kF; ++a)
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                double acc = 0.0;
+#pragma unroll
+                for (int r = 0; r < kF; ++r) acc = fma(E[r][a], w[r][d], acc);
+                c[a][d] = acc;
+              }
+          }
+        }
+      }
+
+      // ---- middle block, solved by both lanes in the coordinates of the top-down lane -------
+      // own contribution -> top-down coordinates; a lane without blocks contributes the boundary
+      // coupling instead (already part of b below), i.e. zeros here.
+#pragma unroll
+      for (int a = 0; a < kF; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b)
+          if ((a + b) & 1) C[tri(a, b)] = side ? -C[tri(a, b)] : C[tri(a, b)];
+#pragma unroll
+        for (int d = 0; d < D; ++d) c[a][d] *= flip[a];
+      }
+      double Sm[10], gm[kF][D];
+      {
+        const int m = mA + 1;                 // actual middle vertex
+        const double Ta = my_time[m - 1], Tb = my_time[m];
+        TimePowers ta, tb;
+        ta.set(Ta);
+        tb.set(Tb);
+        double da[D], db[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          da[d] = my_pos[m * D + d] - my_pos[(m - 1) * D + d];
+          db[d] = my_pos[(m + 1) * D + d] - my_pos[m * D + d];
+        }
+        diag_block(ta, tb, Sm);
+        rhs_block(ta, tb, da, db, gm);
+        if (p.end_derivatives && active) {
+          // boundary couplings that reach the middle block directly (K = 2, or K = 3 bottom side)
+          const long rec = p.sweep_S > 0 ? prob / p.sweep_S : prob;
+          if (m - 1 == 0) {
+            const double* src = p.end_derivatives + (rec * 2 + 0) * (kF * D);
+            double E0[kF][kF];
+            coupling_block(ta, E0);
+#pragma unroll
+            for (int b = 0; b < kF; ++b)
+#pragma unroll
+              for (int d = 0; d < D; ++d)
+#pragma unroll
+                for (int a = 0; a < kF; ++a) gm[b][d] = fma(-E0[a][b], src[a * D + d], gm[b][d]);
+          }
+          if (m + 1 == K) {
+            const double* src = p.end_derivatives + (rec * 2 + 1) * (kF * D);
+            double E1[kF][kF];
+            coupling_block(tb, E1);
+#pragma unroll
+            for (int a = 0; a < kF; ++a)
+#pragma unroll
+              for (int d = 0; d < D; ++d)
+#pragma unroll
+                for (int b = 0; b < kF; ++b) gm[a][d] = fma(-E1[a][b], src[b * D + d], gm[a][d]);
+          }
+        }
+      }
+      {
+        // subtract the top-down contribution first, then the bottom-up one, on both lanes
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const double other = __shfl_xor_sync(0xffffffffu, C[i], 1);
+          const double cA = side ? other : C[i];
+          const double cB = side ? C[i] : other;
+          Sm[i] = (Sm[i] - cA) - cB;
+        }
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const double other = __shfl_xor_sync(0xffffffffu, c[a][d], 1);
+            const double cA = side ? other : c[a][d];
+            const double cB = side ? c[a][d] : other;
+            gm[a][d] = (gm[a][d] - cA) - cB;
+          }
+        double L[10], inv[4];
+        if (!ldlt4(Sm, L, inv)) status |= 1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          double col[4] = {gm[0][d], gm[1][d], gm[2][d], gm[3][d]};
+          ldlt4_solve(L, inv, col);
+#pragma unroll
+          for (int a = 0; a < kF; ++a) xm[a][d] = flip[a] * col[a];   // -> local coordinates
+        }
+      }
+      if (p.free_out && active && side == 0 && p.sweep_S == 0) {
+        double* dst = p.free_out + (prob * (long)nb + mA) * (kF * D);
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) dst[a * D + d] = xm[a][d];
+      }
+    } else {
+      // K == 1: no unknowns; the single segment has both ends fixed. Lane 0 recovers it with
+      // the far end = the other boundary.
+#pragma unroll
+      for (int a = 0; a < kF; ++a)
+#pragma unroll
+        for (int d = 0; d < D; ++d) xm[a][d] = 0.0;
+      if (p.end_derivatives && active) {
+        const long rec = p.sweep_S > 0 ? prob / p.sweep_S : prob;
+        const double* src = p.end_derivatives + (rec * 2 + 1) * (kF * D);
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) xm[a][d] = src[a * D + d];
+      }
+    }
+
+    // ---- back substitution outwards: x_j = w_j - Z_j x_{j+1}, stored over w_j ----------------
+    if (nb > 0) {
+      double x_far[kF][D];
+#pragma unroll
+      for (int a = 0; a < kF; ++a)
+#pragma unroll
+        for (int d = 0; d < D; ++d) x_far[a][d] = xm[a][d];
+      for (int j = mA; j >= 1; --j) {
+        const int jj = side ? j - (mA - nB) : j;
+        if (jj >= 1) {
+          double x_near[kF][D];
+#pragma unroll
+          for (int a = 0; a < kF; ++a) {
+            double zrow[kF];
+#pragma unroll
+            for (int b = 0; b < kF; ++b)
+              zrow[b] = my_slots[(z_off + (jj - 1) * kBlockSlots + a * kF + b) * kSlotStride];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              double acc = my_slots[(x_off + (jj - 1) * kF * D + a * D + d) * kSlotStride];
+#pragma unroll
+              for (int b = 0; b < kF; ++b) acc = fma(-zrow[b], x_far[b][d], acc);
+              x_near[a][d] = acc;
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < kF; ++a)
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              my_slots[(x_off + (jj - 1) * kF * D + a * D + d) * kSlotStride] = x_near[a][d];
+              x_far[a][d] = x_near[a][d];
+            }
+          if (p.free_out && active && p.sweep_S == 0) {
+            const int v = side ? K - jj : jj;    // actual vertex
+            double* dst = p.free_out + (prob * (long)nb + (v - 1)) * (kF * D);
+#pragma unroll
+            for (int a = 0; a < kF; ++a)
+#pragma unroll
+              for (int d = 0; d < D; ++d) dst[a * D + d] = flip[a] * x_near[a][d];
+          }
+        }
+      }
+    }
+    __syncwarp();   // all Z blocks are dead from here on: their slots become the coefficient staging area
+
+    // ---- coefficient recovery / cost, one local segment per step ------------------------------
+    // Local segment jj lies between local vertices jj (towards the boundary) and jj+1 (towards
+    // the middle).  The top-down lane owns jj = mA..0, the bottom-up lane jj = nB..0 (its last
+    // step is idle when nB < mA).
+    double cost_acc = 0.0;
+    int nonfinite = 0;
+    const int top = nb > 0 ? mA : 0;
+    const int n_steps = top + 1;
+    for (int step = 0; step < n_steps; ++step) {
+      const int j = top - step;
+      const int jj = side ? j - (mA - nB) : j;
+      const bool mine = active && jj >= 0 && (nb > 0 || side == 0);
+      double x_near[kF][D], x_far[kF][D];
+#pragma unroll
+      for (int a = 0; a < kF; ++a)
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          x_near[a][d] = (jj >= 1) ? my_slots[(x_off + (jj - 1) * kF * D + a * D + d) * kSlotStride] : bd[a][d];
+          x_far[a][d] = (jj >= 0 && jj + 1 <= my_n) ? my_slots[(x_off + jj * kF * D + a * D + d) * kSlotStride]
+                                                   : xm[a][d];
+        }
+
+      // segment in ACTUAL orientation: start = lower vertex index
+      const int jc = jj >= 0 ? jj : 0;
+      const int seg = side ? K - 1 - jc : jc;
+      const double T = my_time[seg];
+      if (!(T > 0.0)) status |= 2;   // MINSNAP_STATUS_BAD_TIME; the two lanes cover all K segments
+      double u[2 * kF + 1][D];   // [dp, T^k start_k (k=1..4), T^k end_k (k=1..4)]
+      double ds[kF][D];          // start derivatives (actual)
+      {
+        const double T2 = T * T, T3 = T2 * T, T4 = T2 * T2;
+        const double tk[kF] = {T, T2, T3, T4};
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const double s_val = side ? flip[a] * x_far[a][d] : x_near[a][d];
+            const double e_val = side ? flip[a] * x_near[a][d] : x_far[a][d];
+            ds[a][d] = s_val;
+            u[1 + a][d] = tk[a] * s_val;
+            u[1 + kF + a][d] = tk[a] * e_val;
+          }
+#pragma unroll
+        for (int d = 0; d < D; ++d) u[0][d] = my_pos[(seg + 1) * D + d] - my_pos[seg * D + d];
+      }
+      const double i1 = fast_rcp(T);
+      const double i2 = i1 * i1, i4 = i2 * i2, i5 = i4 * i1;
+      if (kCoeffs) {
+        const double ipow[5] = {i5, i5 * i1, i5 * i2, i4 * i4, i4 * i5};   // T^-5 .. T^-9
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          double cf[kN];
+          cf[0] = my_pos[seg * D + d];
+#pragma unroll
+          for (int a = 0; a < kF; ++a) cf[1 + a] = A1T(1 + a, 1 + a) * ds[a][d];
+#pragma unroll
+          for (int i = 5; i < kN; ++i) {
+            double acc = A1T(i, 5) * u[0][d];
+#pragma unroll
+            for (int a = 0; a < kF; ++a) {
+              acc = fma(A1T(i, 1 + a), u[1 + a][d], acc);
+              acc = fma(A1T(i, 6 + a), u[1 + kF + a][d], acc);
+            }
+            cf[i] = acc * ipow[i - 5];
+          }
+#pragma unroll
+          for (int i = 0; i < kN; ++i) {
+            if (!isfinite(cf[i])) nonfinite = 1;
+            my_slots[(z_off + d * kN + i) * kSlotStride] = cf[i];
+          }
+        }
+      }
+      if (p.cost && mine) {
+        // u^T Hred1 u * T^-7: the per-segment quadratic form in scaled variables
+        const double i7 = i5 * i2;
+        double qsum = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          double qd = 0.0;
+#pragma unroll
+          for (int r = 0; r < 2 * kF + 1; ++r) {
+            const int hr = r == 0 ? 5 : (r <= kF ? r : r + 1);       // row of H1: dp -> 5, start k -> k, end k -> 5 + k
+            double row = 0.0;
+#pragma unroll
+            for (int s = 0; s < 2 * kF + 1; ++s) {
+              const int hs = s == 0 ? 5 : (s <= kF ? s : s + 1);
+              row = fma(H1T(hr, hs), u[s][d], row);
+            }
+            qd = fma(row, u[r][d], qd);
+          }
+          qsum += qd;
+        }
+        cost_acc = fma(qsum, i7, cost_acc);
+      }
+      if (kCoeffs) {
+        __syncwarp();
+        // cooperative, coalesced copy of the 32 staged records (D*N doubles each) to HBM
+        constexpr int REC = D * kN;
+        for (int e = lane; e < kWarp * REC; e += kWarp) {
+          const int r = e / REC, o = e - r * REC;
+          const int r_side = r & 1, r_q = r >> 1;
+          const int r_jj = r_side ? j - (mA - nB) : j;
+          const bool r_valid = r_q < n_here && r_jj >= 0 && (nb > 0 || r_side == 0);
+          if (r_valid) {
+            const int r_seg = r_side ? K - 1 - r_jj : r_jj;
+            p.coeffs[((base + r_q) * K + r_seg) * REC + o] = slots[(z_off + o) * kSlotStride + r];
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    if (p.cost) {
+      cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, 1);
+      if (active && side == 0) p.cost[prob] = 0.5 * cost_acc;
+    }
+    if (nonfinite) status |= 4;
+    status |= __shfl_xor_sync(0xffffffffu, status, 1);
+    if (p.status && active && side == 0) p.status[prob] = status;
+  }
+}
+
+#undef H1T
+#undef A1T
+
+inline bool supported(int K, int D, int N, int derivative) {
+  return N == 10 && derivative == 4 && K >= 1 && K <= kMaxK && D >= 1 && D <= 3;
+}
+inline bool sweep_supported(int K, int D, int N, int derivative) { return supported(K, D, N, derivative); }
+
+template <int D, bool kCoeffs>
+inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
+  const size_t per_warp = warp_smem_doubles<D>(p.K) * sizeof(double);
+  int warps = 4;
+  while (warps > 1 && per_warp * warps > kMaxDynamicSmem) warps >>= 1;
+  if (per_warp * warps > kMaxDynamicSmem) return cudaErrorInvalidConfiguration;
+  const size_t smem = per_warp * warps;
+  auto kernel = solve_standard_pair_kernel<D, kCoeffs>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long n_problems = p.sweep_S > 0 ? p.B * p.sweep_S : p.B;
+  const long per_cta = (long)warps * kPairsPerWarp;
+  long grid = (n_problems + per_cta - 1) / per_cta;
+  const long max_grid = 148L * 64;
+  if (grid > max_grid) grid = max_grid;
+  kernel<<<(int)grid, warps * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch(const StandardSolveArgs& a, cudaStream_t stream) {
+  FastParams p;
+  p.B = a.B; p.K = a.K; p.positions = a.d_positions; p.end_derivatives = a.d_end_derivatives;
+  p.times = a.d_times; p.v_max = a.v_max; p.a_max = a.a_max; p.magic = a.magic; p.times_out = a.d_times_out;
+  p.coeffs = a.d_coeffs; p.free_out = a.d_free_out; p.cost = a.d_cost; p.status = a.d_status; p.sweep_S = 0;
+  switch (a.D) {
+    case 1: return launch_d<1, true>(p, stream);
+    case 2: return launch_d<2, true>(p, stream);
+    case 3: return launch_d<3, true>(p, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+inline cudaError_t launch_sweep(const SweepArgs& a, cudaStream_t stream) {
+  FastParams p;
+  p.B = a.B; p.K = a.K; p.positions = a.d_positions; p.end_derivatives = a.d_end_derivatives;
+  p.times = a.d_times; p.v_max = 0; p.a_max = 0; p.magic = 0; p.times_out = nullptr;
+  p.coeffs = nullptr; p.free_out = nullptr; p.cost = a.d_cost; p.status = a.d_status; p.sweep_S = a.S;
+  switch (a.D) {
+    case 1: return launch_d<1, false>(p, stream);
+    case 2: return launch_d<2, false>(p, stream);
+    case 3: return launch_d<3, false>(p, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
 
 }  // namespace fast
 }  // namespace minsnap
