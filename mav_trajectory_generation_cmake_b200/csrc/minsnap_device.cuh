@@ -12,7 +12,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define MINSNAP_TABLE_QUAL static __device__
+// __constant__: kernels that index the tables with compile-time constants get c[bank][offset]
+// operands straight into DFMA/DMUL (no loads, no immediate moves)
+#define MINSNAP_TABLE_QUAL static __constant__
 #include "minsnap_tables.h"
 
 namespace minsnap {

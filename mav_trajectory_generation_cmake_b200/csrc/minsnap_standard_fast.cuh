@@ -27,6 +27,8 @@
 // warp-wide loads into shared memory, coefficients are transposed through shared memory and
 // written as full 16-byte-per-lane coalesced stores.
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "minsnap_device.cuh"
 #include "minsnap_launch.h"
 
@@ -142,22 +144,35 @@ struct FastParams {
   double* cost;
   int32_t* status;
   int sweep_S;  // > 0: cost-only time sweep, times is [B][S][K]
+  bool aligned16;  // positions / times pointers are 16-byte aligned (16-byte cp.async allowed)
 };
 
 template <int D>
 __host__ __device__ inline int lane_slots(int K) {
   const int mA = (K - 1) / 2;
-  const int a = (kBlockSlots + kF * D) * mA;
-  const int b = kF * D * mA + D * kN;
-  return a > b ? a : b;
+  const int a = (kBlockSlots + kF * D) * mA;   // per eliminated block: Z (16) + w/x (4 D)
+  return a > 2 ? a : 2;
 }
 
 template <int D>
 __host__ __device__ inline size_t warp_smem_doubles(int K) {
-  // [slots][33] + positions [16][(K+1) D | 1] + times [16][K | 1]  (odd strides: conflict-free)
-  const int ps = ((K + 1) * D) | 1;
-  const int ts = K | 1;
-  return (size_t)lane_slots<D>(K) * kSlotStride + (size_t)kPairsPerWarp * (ps + ts);
+  // [slots][33] + positions [16][(K+1) D] + times [16][K]; every region a multiple of 16 bytes
+  const size_t slots = ((size_t)lane_slots<D>(K) * kSlotStride + 1) & ~(size_t)1;
+  const size_t pos = ((size_t)kPairsPerWarp * (K + 1) * D + 1) & ~(size_t)1;
+  const size_t tim = ((size_t)kPairsPerWarp * K + 1) & ~(size_t)1;
+  return slots + pos + tim;
+}
+
+// Warp-cooperative asynchronous copy of n doubles, 16 bytes per cp.async when both pointers
+// are 16-byte aligned.
+__device__ __forceinline__ void async_copy_doubles(double* dst, const double* src, int n, int lane, bool aligned16) {
+  if (aligned16) {
+    const int n2 = n >> 1;
+    for (int e = lane; e < n2; e += kWarp) __pipeline_memcpy_async(dst + 2 * e, src + 2 * e, 16);
+    if ((n & 1) && lane == 0) __pipeline_memcpy_async(dst + n - 1, src + n - 1, 8);
+  } else {
+    for (int e = lane; e < n; e += kWarp) __pipeline_memcpy_async(dst + e, src + e, 8);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -165,17 +180,17 @@ __host__ __device__ inline size_t warp_smem_doubles(int K) {
 // ------------------------------------------------------------------------------------------
 template <int D, bool kCoeffs>
 __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   const int K = p.K;
-  const int pos_stride = ((K + 1) * D) | 1;
-  const int time_stride = K | 1;
+  const int pos_stride = (K + 1) * D;
+  const int time_stride = K;
   double* wbase = smem + (size_t)warp * warp_smem_doubles<D>(K);
   double* slots = wbase;                                                 // [n_slots][33]
-  double* pos_s = slots + (size_t)lane_slots<D>(K) * kSlotStride;        // [16][pos_stride]
-  double* time_s = pos_s + kPairsPerWarp * pos_stride;                   // [16][time_stride]
+  double* pos_s = slots + (((size_t)lane_slots<D>(K) * kSlotStride + 1) & ~(size_t)1);   // [16][pos_stride]
+  double* time_s = pos_s + (((size_t)kPairsPerWarp * pos_stride + 1) & ~(size_t)1);      // [16][time_stride]
 
   const int side = lane & 1;   // 0: top-down lane, 1: bottom-up lane
   const int q = lane >> 1;     // pair index within the warp
@@ -198,26 +213,20 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
     __syncwarp();
     // ---- stage inputs: coalesced global reads, odd-stride shared layout -------------------
     {
+      // Asynchronous global->shared copies (cp.async): every chunk is in flight before the
+      // first one is waited for, so a batch pays the DRAM latency once, not once per chunk.
       const int per_pos = (K + 1) * D;
       if (p.sweep_S > 0) {
         for (int e = lane; e < n_here * per_pos; e += kWarp) {
           const int r = e / per_pos, o = e - r * per_pos;
-          pos_s[r * pos_stride + o] = p.positions[((base + r) / p.sweep_S) * per_pos + o];
+          __pipeline_memcpy_async(pos_s + e, p.positions + ((base + r) / p.sweep_S) * per_pos + o, 8);
         }
       } else {
-        const double* src = p.positions + base * per_pos;
-        for (int e = lane; e < n_here * per_pos; e += kWarp) {
-          const int r = e / per_pos, o = e - r * per_pos;
-          pos_s[r * pos_stride + o] = src[e];
-        }
+        async_copy_doubles(pos_s, p.positions + base * per_pos, n_here * per_pos, lane, p.aligned16);
       }
-      if (p.times) {
-        const double* tsrc = p.times + base * K;
-        for (int e = lane; e < n_here * K; e += kWarp) {
-          const int r = e / K, o = e - r * K;
-          time_s[r * time_stride + o] = tsrc[e];
-        }
-      }
+      if (p.times) async_copy_doubles(time_s, p.times + base * K, n_here * K, lane, p.aligned16);
+      __pipeline_commit();
+      __pipeline_wait_prior(0);
       __syncwarp();
       if (!p.times) {
         // ref estimateSegmentTimes (src/vertex.cpp:162-178), same expression as minsnap_estimate_segment_times
@@ -249,20 +258,12 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
     int status = 0;
     double* my_slots = slots + lane;     // slot s of this lane: my_slots[s * 33]
 
-    // boundary derivatives of the local chain (vertex 0 of the lane), in local coordinates
-    double bd[kF][D];
-#pragma unroll
-    for (int a = 0; a < kF; ++a)
-#pragma unroll
-      for (int d = 0; d < D; ++d) bd[a][d] = 0.0;
-    if (p.end_derivatives && active) {
-      const long rec = p.sweep_S > 0 ? prob / p.sweep_S : prob;
-      const double* src = p.end_derivatives + (rec * 2 + side) * (kF * D);
-#pragma unroll
-      for (int a = 0; a < kF; ++a)
-#pragma unroll
-        for (int d = 0; d < D; ++d) bd[a][d] = flip[a] * src[a * D + d];
-    }
+    // boundary derivatives of the local chain (vertex 0 of the lane), in local coordinates; read
+    // on demand (zero when the caller passed no end derivatives) instead of living in registers
+    const double* bd_src = nullptr;
+    if (p.end_derivatives && active)
+      bd_src = p.end_derivatives + ((p.sweep_S > 0 ? prob / p.sweep_S : prob) * 2 + side) * (kF * D);
+    auto bd = [&](int a, int d) { return bd_src ? flip[a] * bd_src[a * D + d] : 0.0; };
 
     double xm[kF][D];   // middle block solution, local coordinates
     TimePowers tp_prev, tp_next;
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
       };
       diag_block(tp_prev, tp_next, S);
       rhs_block(tp_prev, tp_next, dp_prev, dp_next, g);
-      if (p.end_derivatives) {
+      if (bd_src) {
         double E0[kF][kF];
         coupling_block(tp_prev, E0);
 #pragma unroll
@@ -299,22 +300,16 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
           for (int d = 0; d < D; ++d) {
             double acc = g[b][d];
 #pragma unroll
-            for (int a = 0; a < kF; ++a) acc = fma(-E0[a][b], bd[a][d], acc);
+            for (int a = 0; a < kF; ++a) acc = fma(-E0[a][b], bd(a, d), acc);
             g[b][d] = acc;
           }
       }
 
-      double C[10], c[kF][D];   // Schur contribution of this lane to the middle block
-#pragma unroll
-      for (int i = 0; i < 10; ++i) C[i] = 0.0;
-#pragma unroll
-      for (int a = 0; a < kF; ++a)
-#pragma unroll
-        for (int d = 0; d < D; ++d) c[a][d] = 0.0;
-
       for (int j = 1; j <= mA; ++j) {
         if (j <= my_n) {
           // here: tp_prev = segment j-1, tp_next = segment j, S/g = reduced block j
+          double* zb = my_slots + (z_off + (j - 1) * kBlockSlots) * kSlotStride;
+          double* wb = my_slots + (x_off + (j - 1) * kF * D) * kSlotStride;
           double L[10], inv[4];
           if (!ldlt4(S, L, inv)) status |= 1;
           double E[kF][kF];
@@ -327,7 +322,7 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
 #pragma unroll
             for (int a = 0; a < kF; ++a) {
               Z[a][b] = col[a];
-              my_slots[(z_off + (j - 1) * kBlockSlots + a * kF + b) * kSlotStride] = col[a];
+              zb[(a * kF + b) * kSlotStride] = col[a];
             }
           }
           double w[kF][D];
@@ -338,17 +333,18 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
 #pragma unroll
             for (int a = 0; a < kF; ++a) {
               w[a][d] = col[a];
-              my_slots[(x_off + (j - 1) * kF * D + a * D + d) * kSlotStride] = col[a];
+              wb[(a * D + d) * kSlotStride] = col[a];
             }
           }
-          // advance to block j+1 (or, at the last block of the lane, leave the Schur terms)
-          tp_prev = tp_next;
-#pragma unroll
-          for (int d = 0; d < D; ++d) dp_prev[d] = dp_next[d];
           if (j < my_n) {
+            // advance to block j+1: D_{j+1} - E^T Z,  b_{j+1} - E^T w
+            tp_prev = tp_next;
             tp_next.set(local_T(j + 1));
 #pragma unroll
-            for (int d = 0; d < D; ++d) dp_next[d] = local_p(j + 2, d) - local_p(j + 1, d);
+            for (int d = 0; d < D; ++d) {
+              dp_prev[d] = dp_next[d];
+              dp_next[d] = local_p(j + 2, d) - local_p(j + 1, d);
+            }
             diag_block(tp_prev, tp_next, S);
             rhs_block(tp_prev, tp_next, dp_prev, dp_next, g);
 #pragma unroll
@@ -369,25 +365,37 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
                 for (int r = 0; r < kF; ++r) acc = fma(-E[r][a], w[r][d], acc);
                 g[a][d] = acc;
               }
-          } else {
+          }
+        }
+      }
+
+      // Schur contribution of this lane to the middle block, from its last eliminated block
+      // (tp_next still holds the powers of the lane's last local segment): C = E^T Z, c = E^T w
+      double C[10], c[kF][D];
 #pragma unroll
-            for (int a = 0; a < kF; ++a)
+      for (int i = 0; i < 10; ++i) C[i] = 0.0;
 #pragma unroll
-              for (int b = 0; b <= a; ++b) {
-                double acc = 0.0;
+      for (int a = 0; a < kF; ++a)
 #pragma unroll
-                for (int r = 0; r < kF; ++r) acc = fma(E[r][a], Z[r][b], acc);
-                C[tri(a, b)] = acc;
-              }
+        for (int d = 0; d < D; ++d) c[a][d] = 0.0;
+      if (my_n >= 1) {
+        const double* zb = my_slots + (z_off + (my_n - 1) * kBlockSlots) * kSlotStride;
+        const double* wb = my_slots + (x_off + (my_n - 1) * kF * D) * kSlotStride;
+        double E[kF][kF];
+        coupling_block(tp_next, E);
 #pragma unroll
-            for (int a = 0; a < kF; ++a)
+        for (int r = 0; r < kF; ++r) {
+          double zr[kF], wr[D];
 #pragma unroll
-              for (int d = 0; d < D; ++d) {
-                double acc = 0.0;
+          for (int b = 0; b < kF; ++b) zr[b] = zb[(r * kF + b) * kSlotStride];
 #pragma unroll
-                for (int r = 0; r < kF; ++r) acc = fma(E[r][a], w[r][d], acc);
-                c[a][d] = acc;
-              }
+          for (int d = 0; d < D; ++d) wr[d] = wb[(r * D + d) * kSlotStride];
+#pragma unroll
+          for (int a = 0; a < kF; ++a) {
+#pragma unroll
+            for (int b = 0; b <= a; ++b) C[tri(a, b)] = fma(E[r][a], zr[b], C[tri(a, b)]);
+#pragma unroll
+            for (int d = 0; d < D; ++d) c[a][d] = fma(E[r][a], wr[d], c[a][d]);
           }
         }
       }
@@ -559,7 +567,7 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
       for (int a = 0; a < kF; ++a)
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          x_near[a][d] = (jj >= 1) ? my_slots[(x_off + (jj - 1) * kF * D + a * D + d) * kSlotStride] : bd[a][d];
+          x_near[a][d] = (jj >= 1) ? my_slots[(x_off + (jj - 1) * kF * D + a * D + d) * kSlotStride] : bd(a, d);
           x_far[a][d] = (jj >= 0 && jj + 1 <= my_n) ? my_slots[(x_off + jj * kF * D + a * D + d) * kSlotStride]
                                                    : xm[a][d];
         }
@@ -607,10 +615,20 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
             }
             cf[i] = acc * ipow[i - 5];
           }
+          double chk = 0.0;
 #pragma unroll
-          for (int i = 0; i < kN; ++i) {
-            if (!isfinite(cf[i])) nonfinite = 1;
-            my_slots[(z_off + d * kN + i) * kSlotStride] = cf[i];
+          for (int i = 0; i < kN; ++i) chk = fma(cf[i], 0.0, chk);   // NaN iff any coefficient is non-finite
+          if (chk != 0.0) nonfinite = 1;
+          if (mine) {
+            // the polynomial's 10 coefficients are 80 contiguous, 16-byte aligned bytes of HBM
+            double* dst = p.coeffs + ((prob * K + seg) * D + d) * kN;
+            if (p.aligned16) {
+#pragma unroll
+              for (int i = 0; i < kN; i += 2) __stcs(reinterpret_cast<double2*>(dst + i), make_double2(cf[i], cf[i + 1]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < kN; ++i) __stcs(dst + i, cf[i]);
+            }
           }
         }
       }
@@ -636,22 +654,6 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
         }
         cost_acc = fma(qsum, i7, cost_acc);
       }
-      if (kCoeffs) {
-        __syncwarp();
-        // cooperative, coalesced copy of the 32 staged records (D*N doubles each) to HBM
-        constexpr int REC = D * kN;
-        for (int e = lane; e < kWarp * REC; e += kWarp) {
-          const int r = e / REC, o = e - r * REC;
-          const int r_side = r & 1, r_q = r >> 1;
-          const int r_jj = r_side ? j - (mA - nB) : j;
-          const bool r_valid = r_q < n_here && r_jj >= 0 && (nb > 0 || r_side == 0);
-          if (r_valid) {
-            const int r_seg = r_side ? K - 1 - r_jj : r_jj;
-            p.coeffs[((base + r_q) * K + r_seg) * REC + o] = slots[(z_off + o) * kSlotStride + r];
-          }
-        }
-        __syncwarp();
-      }
     }
 
     if (p.cost) {
@@ -675,8 +677,15 @@ inline bool sweep_supported(int K, int D, int N, int derivative) { return suppor
 template <int D, bool kCoeffs>
 inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
   const size_t per_warp = warp_smem_doubles<D>(p.K) * sizeof(double);
-  int warps = 4;
-  while (warps > 1 && per_warp * warps > kMaxDynamicSmem) warps >>= 1;
+  // warps per CTA that maximise resident warps per SM (shared memory is the limiter; each CTA
+  // also costs 1 KB of reserved shared memory)
+  int warps = 1, best = 0;
+  for (int w = 1; w <= 4; ++w) {
+    const size_t cta = per_warp * w + 1024;
+    if (per_warp * w > kMaxDynamicSmem) break;
+    const int resident = (int)((228 * 1024) / cta) * w;
+    if (resident > best) { best = resident; warps = w; }
+  }
   if (per_warp * warps > kMaxDynamicSmem) return cudaErrorInvalidConfiguration;
   const size_t smem = per_warp * warps;
   auto kernel = solve_standard_pair_kernel<D, kCoeffs>;
@@ -696,6 +705,9 @@ inline cudaError_t launch(const StandardSolveArgs& a, cudaStream_t stream) {
   p.B = a.B; p.K = a.K; p.positions = a.d_positions; p.end_derivatives = a.d_end_derivatives;
   p.times = a.d_times; p.v_max = a.v_max; p.a_max = a.a_max; p.magic = a.magic; p.times_out = a.d_times_out;
   p.coeffs = a.d_coeffs; p.free_out = a.d_free_out; p.cost = a.d_cost; p.status = a.d_status; p.sweep_S = 0;
+  p.aligned16 = (reinterpret_cast<uintptr_t>(a.d_positions) % 16 == 0) &&
+                (reinterpret_cast<uintptr_t>(a.d_times) % 16 == 0) &&
+                (reinterpret_cast<uintptr_t>(a.d_coeffs) % 16 == 0);
   switch (a.D) {
     case 1: return launch_d<1, true>(p, stream);
     case 2: return launch_d<2, true>(p, stream);
@@ -709,6 +721,7 @@ inline cudaError_t launch_sweep(const SweepArgs& a, cudaStream_t stream) {
   p.B = a.B; p.K = a.K; p.positions = a.d_positions; p.end_derivatives = a.d_end_derivatives;
   p.times = a.d_times; p.v_max = 0; p.a_max = 0; p.magic = 0; p.times_out = nullptr;
   p.coeffs = nullptr; p.free_out = nullptr; p.cost = a.d_cost; p.status = a.d_status; p.sweep_S = a.S;
+  p.aligned16 = reinterpret_cast<uintptr_t>(a.d_times) % 16 == 0;
   switch (a.D) {
     case 1: return launch_d<1, false>(p, stream);
     case 2: return launch_d<2, false>(p, stream);
