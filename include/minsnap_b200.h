@@ -182,6 +182,8 @@ MINSNAP_API int minsnap_cost_sweep(long B, int S, int K, int D, int N, int deriv
  * Pinned host buffers (minsnap_host_alloc) make the copies asynchronous. */
 MINSNAP_API int minsnap_host_alloc(void** h_ptr, size_t bytes);
 MINSNAP_API int minsnap_host_free(void* h_ptr);
+MINSNAP_API int minsnap_reorder_host(int N, int K, long n_masks, const uint8_t* h_mask,
+                                     int32_t* h_col_of_row, int32_t* h_counts);
 MINSNAP_API int minsnap_solve_host(long B, int K, int D, int N, int derivative,
                                    const uint8_t* h_fixed_mask, const double* h_fixed_values,
                                    const double* h_times, double* h_coeffs, double* h_free_values,

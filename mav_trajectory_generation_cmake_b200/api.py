@@ -371,3 +371,13 @@ def random_positions_host(B, K, pos_min, pos_max, base_seed):
 # solve_standard runs the single-launch thread-pair kernel for N = 10, snap, K <= 24, D <= 3
 # (csrc/minsnap_standard_fast.cuh); other shapes take the 4-launch generic route.
 STANDARD_FAST_ROUTE = True
+
+
+def reorder_host(masks, N, K):
+    """masks uint8 [n_masks][(K+1)][h] (host) -> (col_of_row [n_masks][N*K], counts [n_masks][2])."""
+    masks = np.ascontiguousarray(masks, np.uint8).reshape(-1, (K + 1) * (N // 2))
+    n = masks.shape[0]
+    col = np.empty((n, N * K), np.int32)
+    counts = np.empty((n, 2), np.int32)
+    capi.check(_lib().minsnap_reorder_host(N, K, n, _hptr(masks), _hptr(col), _hptr(counts)), "minsnap_reorder_host")
+    return col, counts

@@ -36,6 +36,7 @@ SIGNATURES = {
     "minsnap_cost_sweep": (_i, [_l, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "minsnap_host_alloc": (_i, [_vp, _sz]),
     "minsnap_host_free": (_i, [_vp]),
+    "minsnap_reorder_host": (_i, [_i, _i, _l, _vp, _vp, _vp]),
     "minsnap_solve_host": (_i, [_l, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "minsnap_solve_standard_host": (_i, [_l, _i, _i, _i, _i, _vp, _vp, _vp, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     "minsnap_sample_at_host": (_i, [_l, _i, _i, _i, _vp, _vp, _i, _vp, _l, _i, _vp, _vp]),

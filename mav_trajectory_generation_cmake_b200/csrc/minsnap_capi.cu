@@ -300,6 +300,35 @@ int minsnap_host_free(void* h_ptr) {
   return MINSNAP_OK;
 }
 
+int minsnap_reorder_host(int N, int K, long n_masks, const uint8_t* h_mask, int32_t* h_col_of_row,
+                         int32_t* h_counts) {
+  if (!minsnap::supported_n(N) || K < 1 || n_masks < 0 || !h_mask || !h_col_of_row || !h_counts)
+    return MINSNAP_ERR_ARG;
+  if (n_masks == 0) return MINSNAP_OK;
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = MINSNAP_OK;
+  {
+    Scratch mk, col, cnt;
+    const size_t nm = (size_t)n_masks, nc = (size_t)(K + 1) * (N / 2);
+#define TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #x); goto done; } } while (0)
+    TRY(mk.alloc(nm * nc, st));
+    TRY(col.alloc(sizeof(int32_t) * nm * N * K, st));
+    TRY(cnt.alloc(sizeof(int32_t) * nm * 2, st));
+    TRY(cudaMemcpyAsync(mk.ptr, h_mask, nm * nc, cudaMemcpyHostToDevice, st));
+    rc = minsnap_reorder(N, K, n_masks, mk.as<uint8_t>(), col.as<int32_t>(), cnt.as<int32_t>(), st);
+    if (rc != MINSNAP_OK) goto done;
+    TRY(cudaMemcpyAsync(h_col_of_row, col.ptr, sizeof(int32_t) * nm * N * K, cudaMemcpyDeviceToHost, st));
+    TRY(cudaMemcpyAsync(h_counts, cnt.ptr, sizeof(int32_t) * nm * 2, cudaMemcpyDeviceToHost, st));
+#undef TRY
+  done:;
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  return rc;
+}
+
 int minsnap_solve_host(long B, int K, int D, int N, int derivative, const uint8_t* h_fixed_mask,
                        const double* h_fixed_values, const double* h_times, double* h_coeffs,
                        double* h_free_values, double* h_cost, int32_t* h_status, int32_t* h_col_of_row) {

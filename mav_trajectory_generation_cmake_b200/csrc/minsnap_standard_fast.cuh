@@ -205,29 +205,49 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
   const long n_problems = p.sweep_S > 0 ? p.B * p.sweep_S : p.B;
   const long pairs_per_cta = (long)warps_per_cta * kPairsPerWarp;
 
-  for (long base = (long)blockIdx.x * pairs_per_cta + (long)warp * kPairsPerWarp; base < n_problems;
-       base += (long)gridDim.x * pairs_per_cta) {
+  // Asynchronous global->shared input copies (cp.async): every chunk is in flight before the
+  // first one is waited for.  Warps are persistent; the inputs of a warp's NEXT batch are
+  // fetched while it recovers the coefficients of the current one, into the shared-memory
+  // area of the (by then dead) Z blocks, so the DRAM latency is off the critical path.
+  const int per_pos = (K + 1) * D;
+  auto issue_inputs = [&](double* dst_pos, double* dst_time, long b0, int n) {
+    if (p.sweep_S > 0) {
+      for (int e = lane; e < n * per_pos; e += kWarp) {
+        const int r = e / per_pos, o = e - r * per_pos;
+        __pipeline_memcpy_async(dst_pos + e, p.positions + ((b0 + r) / p.sweep_S) * per_pos + o, 8);
+      }
+    } else {
+      async_copy_doubles(dst_pos, p.positions + b0 * per_pos, n * per_pos, lane, p.aligned16);
+    }
+    if (p.times) async_copy_doubles(dst_time, p.times + b0 * K, n * K, lane, p.aligned16);
+    __pipeline_commit();
+  };
+  const int pos_doubles = (kPairsPerWarp * per_pos + 1) & ~1;            // region sizes, even
+  const int time_doubles = (kPairsPerWarp * K + 1) & ~1;
+  double* landing = slots + (size_t)(kF * D * mA) * kSlotStride;          // start of the Z area
+  const bool can_prefetch = kBlockSlots * mA * kSlotStride >= pos_doubles + time_doubles &&
+                            ((kF * D * mA * kSlotStride) & 1) == 0;
+  const long stride = (long)gridDim.x * pairs_per_cta;
+  const long first = (long)blockIdx.x * pairs_per_cta + (long)warp * kPairsPerWarp;
+  bool landed = false;
+  if (first < n_problems) issue_inputs(pos_s, time_s, first, (int)min((long)kPairsPerWarp, n_problems - first));
+
+  for (long base = first; base < n_problems; base += stride) {
     const int n_here = (int)min((long)kPairsPerWarp, n_problems - base);
+    const long next_base = base + stride;
+    const int n_next = next_base < n_problems ? (int)min((long)kPairsPerWarp, n_problems - next_base) : 0;
     const long prob = base + q;          // problem of this pair
     const bool active = q < n_here;
-    __syncwarp();
-    // ---- stage inputs: coalesced global reads, odd-stride shared layout -------------------
+    // ---- inputs of this batch ---------------------------------------------------------------
     {
-      // Asynchronous global->shared copies (cp.async): every chunk is in flight before the
-      // first one is waited for, so a batch pays the DRAM latency once, not once per chunk.
-      const int per_pos = (K + 1) * D;
-      if (p.sweep_S > 0) {
-        for (int e = lane; e < n_here * per_pos; e += kWarp) {
-          const int r = e / per_pos, o = e - r * per_pos;
-          __pipeline_memcpy_async(pos_s + e, p.positions + ((base + r) / p.sweep_S) * per_pos + o, 8);
-        }
-      } else {
-        async_copy_doubles(pos_s, p.positions + base * per_pos, n_here * per_pos, lane, p.aligned16);
-      }
-      if (p.times) async_copy_doubles(time_s, p.times + base * K, n_here * K, lane, p.aligned16);
-      __pipeline_commit();
       __pipeline_wait_prior(0);
       __syncwarp();
+      if (landed) {
+        for (int e = lane; e < n_here * per_pos; e += kWarp) pos_s[e] = landing[e];
+        if (p.times)
+          for (int e = lane; e < n_here * K; e += kWarp) time_s[e] = landing[pos_doubles + e];
+        __syncwarp();
+      }
       if (!p.times) {
         // ref estimateSegmentTimes (src/vertex.cpp:162-178), same expression as minsnap_estimate_segment_times
         for (int e = lane; e < n_here * K; e += kWarp) {
@@ -548,7 +568,11 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
         }
       }
     }
-    __syncwarp();   // all Z blocks are dead from here on: their slots become the coefficient staging area
+    __syncwarp();   // all Z blocks are dead from here on: their slots receive the next batch's inputs
+    if (n_next > 0 && can_prefetch) {
+      issue_inputs(landing, landing + pos_doubles, next_base, n_next);
+      landed = true;
+    }
 
     // ---- coefficient recovery / cost, one local segment per step ------------------------------
     // Local segment jj lies between local vertices jj (towards the boundary) and jj+1 (towards
@@ -663,6 +687,11 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
     if (nonfinite) status |= 4;
     status |= __shfl_xor_sync(0xffffffffu, status, 1);
     if (p.status && active && side == 0) p.status[prob] = status;
+    if (n_next > 0 && !can_prefetch) {
+      __syncwarp();   // every lane is done with this batch's inputs
+      issue_inputs(pos_s, time_s, next_base, n_next);
+      landed = false;
+    }
   }
 }
 
@@ -694,7 +723,10 @@ inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
   const long n_problems = p.sweep_S > 0 ? p.B * p.sweep_S : p.B;
   const long per_cta = (long)warps * kPairsPerWarp;
   long grid = (n_problems + per_cta - 1) / per_cta;
-  const long max_grid = 148L * 64;
+  // One batch of 16 trajectories per warp while the grid stays modest: the hardware CTA scheduler
+  // then balances the SMs dynamically (measured: a fixed persistent grid loses ~8% to the
+  // 4.6-batches-per-slot tail at 65,536 problems).  Very large batches loop with prefetch.
+  const long max_grid = 148L * 256;
   if (grid > max_grid) grid = max_grid;
   kernel<<<(int)grid, warps * 32, smem, stream>>>(p);
   return cudaGetLastError();
