@@ -197,7 +197,8 @@ def run_gpu_arm(args):
     ms.load()
     B = B_PER_GPU
     # each rank owns a contiguous slice of the global batch: seeds 12345 + rank*B + b
-    pos_h = ms.random_positions_host(B, K_SEG, BOX_LO, BOX_HI, BASE_SEED + rank * B)
+    from mav_trajectory_generation_cmake_b200.sharding import gather_to_rank0, weak_scaling_seed_base
+    pos_h = ms.random_positions_host(B, K_SEG, BOX_LO, BOX_HI, weak_scaling_seed_base(BASE_SEED, B, rank))
     n_sets = 2   # rotate buffer sets so a step never finds its inputs in L2 (2 x 180 MB > 126 MB)
     pos_d = [torch.from_numpy(pos_h).cuda() for _ in range(n_sets)]
     times_d = [ms.estimate_segment_times(p, V_MAX, A_MAX, MAGIC) for p in pos_d]
@@ -258,14 +259,14 @@ def run_gpu_arm(args):
     # ---- optional: one NCCL gather of the coefficient blocks (reported separately) ------------
     gather_ms = None
     if distributed:
-        out = [torch.empty_like(coeffs_d[0]) for _ in range(world)] if rank == 0 else None
-        dist.gather(coeffs_d[0], out, dst=0)
+        gather_to_rank0(coeffs_d[0], world * B, dist)
         torch.cuda.synchronize()
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        dist.gather(coeffs_d[0], out, dst=0)
+        gathered = gather_to_rank0(coeffs_d[0], world * B, dist)
         g1.record()
+        del gathered
         torch.cuda.synchronize()
         t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
