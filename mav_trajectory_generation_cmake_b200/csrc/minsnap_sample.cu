@@ -25,6 +25,7 @@ struct SampleKernelParams {
   double* out;
   double* t_out;
   int32_t* segment;
+  bool out_aligned16 = false;
 };
 
 constexpr int kSampleThreads = 128;
@@ -143,10 +144,137 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleKernelPara
   }
 }
 
+// =========================================================================================
+// Derivatives 0..ND-1 in ONE pass over the raw coefficients (complete Horner scheme /
+// repeated synthetic division): after pass k, a[k] = p^(k)(t) / k!.  Same 35 FMAs per
+// dimension as five separate Horner runs over b(k,j) c_j (ref polynomial.h:138-151), but only
+// N coefficient loads per polynomial instead of sum_k (N-k): the kernel stops being bound by
+// shared-memory loads and becomes HBM-write bound.  Stores are 16 bytes per lane.
+// Shared memory: acc_end[K] | seg_start[K] | coef[K][D][N] | stage[warps][32][ND*D] (16-B aligned)
+// =========================================================================================
+template <int N, int ND>
+__global__ void __launch_bounds__(kSampleThreads) sample_all_derivatives_kernel(SampleKernelParams p) {
+  extern __shared__ __align__(16) double smem[];
+  const int K = p.K, D = p.D;
+  const int per = ND * D;
+  const int n_c = K * D * N;
+  double* acc_end = smem;
+  double* seg_start = acc_end + K;
+  double* coef = seg_start + K;
+  double* stage = coef + n_c + ((2 * K + n_c) & 1);   // keep the staging area 16-byte aligned
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double* my_stage = stage + (size_t)warp * kWarp * per + ((warp * kWarp * per) & 1);
+  constexpr double kFactorial[6] = {1.0, 1.0, 2.0, 6.0, 24.0, 120.0};
+
+  const long n_work = p.B * p.chunks;
+  for (long w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const long b = w / p.chunks;
+    const int chunk = (int)(w - b * p.chunks);
+    const double* cb = p.coeffs + b * (long)n_c;
+    const double* Tb = p.times + b * K;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n_c; e += blockDim.x) coef[e] = cb[e];
+    if (threadIdx.x == 0) {
+      double acc = 0.0;
+      for (int i = 0; i < K; ++i) {
+        acc += Tb[i];
+        acc_end[i] = acc;
+        seg_start[i] = acc - Tb[i];   // (acc + T_i) - T_i, as the reference (src/trajectory.cpp:46-63)
+      }
+    }
+    __syncthreads();
+    const double total = acc_end[K - 1];
+    const double dt = total / (double)p.M;
+    const int m_begin = chunk * p.chunk_len;
+    const int m_end = min(p.M, m_begin + p.chunk_len);
+    for (int m0 = m_begin + warp * kWarp; m0 < m_end; m0 += kSampleWarps * kWarp) {
+      const int m = m0 + lane;
+      const bool valid = m < m_end;
+      if (valid) {
+        const double t = p.t_in ? p.t_in[b * p.t_stride + m] : (double)m * dt;
+        int seg = find_segment(acc_end, K, t);
+        if (seg >= K || !(t == t)) seg = -1;
+        const double tl = seg >= 0 ? t - seg_start[seg] : 0.0;
+        const double* cs = coef + (size_t)(seg >= 0 ? seg : 0) * D * N;
+        for (int dim = 0; dim < D; ++dim) {
+          double a[N];
+#pragma unroll
+          for (int j = 0; j < N; ++j) a[j] = cs[dim * N + j];
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            if (k < N) {
+#pragma unroll
+              for (int j = N - 2; j >= k; --j) a[j] = fma(a[j + 1], tl, a[j]);
+              double f = kFactorial[k < 6 ? k : 5];
+              if (k >= 6)
+                for (int q = 6; q <= k; ++q) f *= (double)q;
+              my_stage[lane * per + k * D + dim] = seg >= 0 ? a[k] * f : 0.0;
+            } else {
+              my_stage[lane * per + k * D + dim] = 0.0;
+            }
+          }
+        }
+        if (p.t_out) p.t_out[b * (long)p.M + m] = t;
+        if (p.segment) p.segment[b * (long)p.M + m] = seg;
+      }
+      __syncwarp();
+      const int n_valid = min(kWarp, m_end - m0);
+      const long first = (b * (long)p.M + m0) * per;
+      double* dst = p.out + first;
+      const int count = n_valid * per;
+      if (((first | count) & 1) == 0 && p.out_aligned16) {
+        const double2* src2 = reinterpret_cast<const double2*>(my_stage);
+        double2* dst2 = reinterpret_cast<double2*>(dst);
+        for (int e = lane; e < count / 2; e += kWarp) __stcs(dst2 + e, src2[e]);
+      } else {
+        for (int e = lane; e < count; e += kWarp) __stcs(dst + e, my_stage[e]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 template <int N>
 static cudaError_t launch_sample_n(const SampleArgs& a, cudaStream_t stream) {
   if (a.B == 0 || a.M == 0) return cudaSuccess;
   const int per = a.n_deriv * a.D;
+  // fast kernel: n_deriv <= 5 and the raw coefficients of one trajectory fit shared memory
+  {
+    const size_t n_c = (size_t)a.K * a.D * N;
+    const size_t doubles = 2 * (size_t)a.K + n_c + 1 + (size_t)kSampleWarps * (kWarp * per + 1);
+    const size_t smem_fast = doubles * sizeof(double);
+    if (a.n_deriv <= 5 && smem_fast <= 96 * 1024) {
+      SampleKernelParams p;
+      p.B = a.B; p.K = a.K; p.D = a.D; p.M = a.M; p.n_deriv = a.n_deriv;
+      int chunk_len = a.M;
+      if (a.B < 148L * 8) {
+        const long want = (148L * 8 + a.B - 1) / a.B;
+        chunk_len = (int)((a.M + want - 1) / want);
+        if (chunk_len < kSampleThreads) chunk_len = kSampleThreads;
+        chunk_len = (chunk_len + kWarp - 1) / kWarp * kWarp;
+      }
+      p.chunk_len = chunk_len;
+      p.chunks = (a.M + chunk_len - 1) / chunk_len;
+      p.coeffs = a.d_coeffs; p.times = a.d_times; p.t_in = a.d_t; p.t_stride = a.t_stride;
+      p.out = a.d_out; p.t_out = a.d_t_out; p.segment = a.d_segment;
+      p.out_aligned16 = reinterpret_cast<uintptr_t>(a.d_out) % 16 == 0;
+      long grid = a.B * p.chunks;
+      if (grid > (1L << 30)) grid = 1L << 30;
+      void (*kernel)(SampleKernelParams) = nullptr;
+      switch (a.n_deriv) {
+        case 1: kernel = sample_all_derivatives_kernel<N, 1>; break;
+        case 2: kernel = sample_all_derivatives_kernel<N, 2>; break;
+        case 3: kernel = sample_all_derivatives_kernel<N, 3>; break;
+        case 4: kernel = sample_all_derivatives_kernel<N, 4>; break;
+        default: kernel = sample_all_derivatives_kernel<N, 5>; break;
+      }
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
+      if (e != cudaSuccess) return e;
+      kernel<<<(unsigned)grid, kSampleThreads, smem_fast, stream>>>(p);
+      return cudaGetLastError();
+    }
+  }
   const size_t base = sizeof(double) * ((size_t)2 * a.K + (size_t)kSampleWarps * kWarp * per);
   const size_t staged = base + sizeof(double) * (size_t)a.n_deriv * a.K * a.D * N;
   const bool use_staged = staged <= 64 * 1024;
