@@ -8,7 +8,11 @@
 //     (any N, K, D, derivative the general path supports).
 #include "minsnap_device.cuh"
 #include "minsnap_launch.h"
+#include <cstdlib>
+#include <cstring>
+
 #include "minsnap_standard_fast.cuh"
+#include "minsnap_standard_ws.cuh"
 
 namespace minsnap {
 
@@ -91,6 +95,29 @@ static cudaError_t generic_route(long B, int S, int K, int D, int N, int derivat
 
 bool standard_supported(int K, int D, int N, int derivative) { return fast::supported(K, D, N, derivative); }
 
+// Kernel choice for the fast route: the two-lane kernel (default) or the warp-specialised CTA
+// (MINSNAP_STANDARD_KERNEL=ws; correct, parity-tested, but measured slower on B200: its matrix
+// warp and dimension warps idle on each other and the per-warp overheads triple).
+static bool use_ws_kernel(int K, int D, int N, int derivative) {
+  if (!ws::supported(K, D, N, derivative)) return false;
+  const char* v = std::getenv("MINSNAP_STANDARD_KERNEL");
+  return v && std::strcmp(v, "ws") == 0;
+}
+
+static cudaError_t launch_fast_route(const fast::FastParams& p, int D, bool coeffs, bool ws_kernel, cudaStream_t stream) {
+#define MINSNAP_FAST_CASE(D_)                                                                         \
+  case D_:                                                                                            \
+    if (ws_kernel) return coeffs ? ws::launch_d<D_, true>(p, stream) : ws::launch_d<D_, false>(p, stream); \
+    return coeffs ? fast::launch_d<D_, true>(p, stream) : fast::launch_d<D_, false>(p, stream);
+  switch (D) {
+    MINSNAP_FAST_CASE(1)
+    MINSNAP_FAST_CASE(2)
+    MINSNAP_FAST_CASE(3)
+    default: return cudaErrorInvalidValue;
+  }
+#undef MINSNAP_FAST_CASE
+}
+
 cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t stream) {
   if (a.B == 0) return cudaSuccess;
   AsyncBuffer times_scratch;
@@ -109,14 +136,30 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
       return e;
     times = dst;
   }
-  if (fast_ok) return fast::launch(a, stream);
+  if (fast_ok) {
+    fast::FastParams p;
+    p.B = a.B; p.K = a.K; p.positions = a.d_positions; p.end_derivatives = a.d_end_derivatives;
+    p.times = a.d_times; p.v_max = a.v_max; p.a_max = a.a_max; p.magic = a.magic; p.times_out = a.d_times_out;
+    p.coeffs = a.d_coeffs; p.free_out = a.d_free_out; p.cost = a.d_cost; p.status = a.d_status; p.sweep_S = 0;
+    p.aligned16 = (reinterpret_cast<uintptr_t>(a.d_positions) % 16 == 0) &&
+                  (reinterpret_cast<uintptr_t>(a.d_times) % 16 == 0) &&
+                  (reinterpret_cast<uintptr_t>(a.d_coeffs) % 16 == 0);
+    return launch_fast_route(p, a.D, true, use_ws_kernel(a.K, a.D, a.N, a.derivative), stream);
+  }
   return generic_route(a.B, 1, a.K, a.D, a.N, a.derivative, a.d_positions, a.d_end_derivatives, times, a.d_coeffs,
                        a.d_free_out, a.d_cost, a.d_status, stream);
 }
 
 cudaError_t launch_cost_sweep(const SweepArgs& a, cudaStream_t stream) {
   if (a.B == 0) return cudaSuccess;
-  if (fast::sweep_supported(a.K, a.D, a.N, a.derivative)) return fast::launch_sweep(a, stream);
+  if (fast::sweep_supported(a.K, a.D, a.N, a.derivative)) {
+    fast::FastParams p;
+    p.B = a.B; p.K = a.K; p.positions = a.d_positions; p.end_derivatives = a.d_end_derivatives;
+    p.times = a.d_times; p.v_max = 0; p.a_max = 0; p.magic = 0; p.times_out = nullptr;
+    p.coeffs = nullptr; p.free_out = nullptr; p.cost = a.d_cost; p.status = a.d_status; p.sweep_S = a.S;
+    p.aligned16 = reinterpret_cast<uintptr_t>(a.d_times) % 16 == 0;
+    return launch_fast_route(p, a.D, false, use_ws_kernel(a.K, a.D, a.N, a.derivative), stream);
+  }
   return generic_route(a.B, a.S, a.K, a.D, a.N, a.derivative, a.d_positions, a.d_end_derivatives, a.d_times, nullptr,
                        nullptr, a.d_cost, a.d_status, stream);
 }

@@ -38,7 +38,7 @@ namespace fast {
 constexpr int kN = 10;          // coefficients per polynomial
 constexpr int kF = 4;           // free derivatives per interior vertex (k = 1..4)
 constexpr int kPairsPerWarp = 16;
-constexpr int kSlotStride = 33; // doubles between consecutive slots of one lane
+constexpr int kSlotStride = 32; // doubles between consecutive slots of one lane ([slot][lane])
 constexpr int kBlockSlots = kF * kF;  // Z of one block
 constexpr int kMaxK = 24;
 
@@ -151,7 +151,8 @@ template <int D>
 __host__ __device__ inline int lane_slots(int K) {
   const int mA = (K - 1) / 2;
   const int a = (kBlockSlots + kF * D) * mA;   // per eliminated block: Z (16) + w/x (4 D)
-  return a > 2 ? a : 2;
+  const int b = kF * D * mA + 2 * kF * D;      // x area + boundary and middle vectors (recovery phase)
+  return a > b ? a : b;
 }
 
 template <int D>
@@ -224,9 +225,12 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
   };
   const int pos_doubles = (kPairsPerWarp * per_pos + 1) & ~1;            // region sizes, even
   const int time_doubles = (kPairsPerWarp * K + 1) & ~1;
-  double* landing = slots + (size_t)(kF * D * mA) * kSlotStride;          // start of the Z area
-  const bool can_prefetch = kBlockSlots * mA * kSlotStride >= pos_doubles + time_doubles &&
-                            ((kF * D * mA * kSlotStride) & 1) == 0;
+  // landing zone of the prefetch: the Z area minus its first 2*kF*D slots (those hold the
+  // boundary / middle vectors during coefficient recovery)
+  const int landing_slot = kF * D * mA + 2 * kF * D;
+  double* landing = slots + (size_t)landing_slot * kSlotStride;
+  const bool can_prefetch = (kBlockSlots * mA - 2 * kF * D) * kSlotStride >= pos_doubles + time_doubles &&
+                            ((landing_slot * kSlotStride) & 1) == 0;
   const long stride = (long)gridDim.x * pairs_per_cta;
   const long first = (long)blockIdx.x * pairs_per_cta + (long)warp * kPairsPerWarp;
   bool landed = false;
@@ -550,11 +554,13 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
               x_near[a][d] = acc;
             }
           }
+          // x is stored in ACTUAL coordinates (odd derivatives of the bottom-up lane flipped)
+          // so that the recovery below reads start / end vectors without any sign logic
 #pragma unroll
           for (int a = 0; a < kF; ++a)
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-              my_slots[(x_off + (jj - 1) * kF * D + a * D + d) * kSlotStride] = x_near[a][d];
+              my_slots[(x_off + (jj - 1) * kF * D + a * D + d) * kSlotStride] = flip[a] * x_near[a][d];
               x_far[a][d] = x_near[a][d];
             }
           if (p.free_out && active && p.sweep_S == 0) {
@@ -568,6 +574,16 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
         }
       }
     }
+    // boundary and middle vectors (actual coordinates) join the x's in shared memory, in two
+    // groups of the now dead Z area, so every end-point vector is read the same way
+    const int bd_slot = z_off, xm_slot = z_off + kF * D;
+#pragma unroll
+    for (int a = 0; a < kF; ++a)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        my_slots[(bd_slot + a * D + d) * kSlotStride] = bd_src ? bd_src[a * D + d] : 0.0;
+        my_slots[(xm_slot + a * D + d) * kSlotStride] = flip[a] * xm[a][d];
+      }
     __syncwarp();   // all Z blocks are dead from here on: their slots receive the next batch's inputs
     if (n_next > 0 && can_prefetch) {
       issue_inputs(landing, landing + pos_doubles, next_base, n_next);
@@ -586,18 +602,13 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
       const int j = top - step;
       const int jj = side ? j - (mA - nB) : j;
       const bool mine = active && jj >= 0 && (nb > 0 || side == 0);
-      double x_near[kF][D], x_far[kF][D];
-#pragma unroll
-      for (int a = 0; a < kF; ++a)
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          x_near[a][d] = (jj >= 1) ? my_slots[(x_off + (jj - 1) * kF * D + a * D + d) * kSlotStride] : bd(a, d);
-          x_far[a][d] = (jj >= 0 && jj + 1 <= my_n) ? my_slots[(x_off + jj * kF * D + a * D + d) * kSlotStride]
-                                                   : xm[a][d];
-        }
-
-      // segment in ACTUAL orientation: start = lower vertex index
+      // end-point vectors of the segment in ACTUAL orientation (start = lower vertex index): the
+      // vector of local vertex v lives at slot group  v == 0 ? boundary : v <= my_n ? x_v : middle
       const int jc = jj >= 0 ? jj : 0;
+      const int near_slot = jc >= 1 ? x_off + (jc - 1) * kF * D : bd_slot;
+      const int far_slot = jc + 1 <= my_n ? x_off + jc * kF * D : xm_slot;
+      const double* start_ptr = my_slots + (side ? far_slot : near_slot) * kSlotStride;
+      const double* end_ptr = my_slots + (side ? near_slot : far_slot) * kSlotStride;
       const int seg = side ? K - 1 - jc : jc;
       const double T = my_time[seg];
       if (!(T > 0.0)) status |= 2;   // MINSNAP_STATUS_BAD_TIME; the two lanes cover all K segments
@@ -610,8 +621,8 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
         for (int a = 0; a < kF; ++a)
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            const double s_val = side ? flip[a] * x_far[a][d] : x_near[a][d];
-            const double e_val = side ? flip[a] * x_near[a][d] : x_far[a][d];
+            const double s_val = start_ptr[(a * D + d) * kSlotStride];
+            const double e_val = end_ptr[(a * D + d) * kSlotStride];
             ds[a][d] = s_val;
             u[1 + a][d] = tk[a] * s_val;
             u[1 + kF + a][d] = tk[a] * e_val;
