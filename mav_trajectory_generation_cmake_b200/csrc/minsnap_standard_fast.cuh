@@ -111,6 +111,48 @@ __device__ __forceinline__ void ldlt4_solve(const double (&l)[10], const double 
   y[0] = fma(-l[tri(3, 0)], y[3], fma(-l[tri(2, 0)], y[2], fma(-l[tri(1, 0)], y[1], y[0])));
 }
 
+// Inverse of a symmetric positive definite 4x4 (packed lower triangles) through its 2x2 blocks:
+//   S = [A B^T; B C],  Sigma = C - B A^-1 B^T,
+//   S^-1 = [A^-1 + (B A^-1)^T Sigma^-1 (B A^-1),  -(B A^-1)^T Sigma^-1;  -Sigma^-1 B A^-1,  Sigma^-1].
+// Two reciprocals and ~45 multiply-adds of depth ~12, against four serial pivots for L D L^T;
+// the solves that follow become mat-vec products (independent 4-term chains).  Elimination
+// without pivoting on an SPD matrix: the same subtractions L D L^T performs.  Returns false
+// when a leading minor is not positive.
+__device__ __forceinline__ bool spd4_inverse(const double (&s)[10], double (&si)[10]) {
+  const double a00 = s[0], a10 = s[1], a11 = s[2];
+  const double b00 = s[3], b01 = s[4], c00 = s[5];
+  const double b10 = s[6], b11 = s[7], c10 = s[8], c11 = s[9];
+  const double detA = fma(a00, a11, -(a10 * a10));
+  bool ok = (a00 > 0.0) & (detA > 0.0);
+  const double iA = fast_rcp(detA);
+  const double A00 = a11 * iA, A10 = -a10 * iA, A11 = a00 * iA;
+  const double BA00 = fma(b01, A10, b00 * A00), BA01 = fma(b01, A11, b00 * A10);
+  const double BA10 = fma(b11, A10, b10 * A00), BA11 = fma(b11, A11, b10 * A10);
+  const double g00 = fma(-BA01, b01, fma(-BA00, b00, c00));
+  const double g10 = fma(-BA11, b01, fma(-BA10, b00, c10));
+  const double g11 = fma(-BA11, b11, fma(-BA10, b10, c11));
+  const double detG = fma(g00, g11, -(g10 * g10));
+  ok &= (g00 > 0.0) & (detG > 0.0);
+  const double iG = fast_rcp(detG);
+  const double G00 = g11 * iG, G10 = -g10 * iG, G11 = g00 * iG;
+  const double L00 = -fma(G10, BA10, G00 * BA00), L01 = -fma(G10, BA11, G00 * BA01);
+  const double L10 = -fma(G11, BA10, G10 * BA00), L11 = -fma(G11, BA11, G10 * BA01);
+  si[0] = fma(-BA10, L10, fma(-BA00, L00, A00));
+  si[1] = fma(-BA11, L10, fma(-BA01, L00, A10));
+  si[2] = fma(-BA11, L11, fma(-BA01, L01, A11));
+  si[3] = L00; si[4] = L01; si[5] = G00;
+  si[6] = L10; si[7] = L11; si[8] = G10; si[9] = G11;
+  return ok;
+}
+
+// y = M x for a packed symmetric 4x4 M.
+__device__ __forceinline__ void sym4_apply(const double (&m)[10], const double (&x)[4], double (&y)[4]) {
+  y[0] = fma(m[6], x[3], fma(m[3], x[2], fma(m[1], x[1], m[0] * x[0])));
+  y[1] = fma(m[7], x[3], fma(m[4], x[2], fma(m[2], x[1], m[1] * x[0])));
+  y[2] = fma(m[8], x[3], fma(m[5], x[2], fma(m[4], x[1], m[3] * x[0])));
+  y[3] = fma(m[9], x[3], fma(m[8], x[2], fma(m[7], x[1], m[6] * x[0])));
+}
+
 // Diagonal block D = EE(T_prev) + SS(T_next) in the coordinates of the lane (lower triangle).
 __device__ __forceinline__ void diag_block(const TimePowers& prev, const TimePowers& next, double (&s)[10]) {
 #pragma unroll
@@ -145,6 +187,7 @@ struct FastParams {
   int32_t* status;
   int sweep_S;  // > 0: cost-only time sweep, times is [B][S][K]
   bool aligned16;  // positions / times pointers are 16-byte aligned (16-byte cp.async allowed)
+  double* slot_scratch = nullptr;  // long chains: [warp][slot][lane] block storage in global memory
 };
 
 template <int D>
@@ -156,9 +199,10 @@ __host__ __device__ inline int lane_slots(int K) {
 }
 
 template <int D>
-__host__ __device__ inline size_t warp_smem_doubles(int K) {
-  // [slots][33] + positions [16][(K+1) D] + times [16][K]; every region a multiple of 16 bytes
-  const size_t slots = ((size_t)lane_slots<D>(K) * kSlotStride + 1) & ~(size_t)1;
+__host__ __device__ inline size_t warp_smem_doubles(int K, bool global_slots = false) {
+  // [slots][32] + positions [16][(K+1) D] + times [16][K]; every region a multiple of 16 bytes.
+  // Long chains keep the slots in global memory (coalesced: one 256-byte row per slot).
+  const size_t slots = global_slots ? 0 : ((size_t)lane_slots<D>(K) * kSlotStride + 1) & ~(size_t)1;
   const size_t pos = ((size_t)kPairsPerWarp * (K + 1) * D + 1) & ~(size_t)1;
   const size_t tim = ((size_t)kPairsPerWarp * K + 1) & ~(size_t)1;
   return slots + pos + tim;
@@ -179,7 +223,7 @@ __device__ __forceinline__ void async_copy_doubles(double* dst, const double* sr
 // ------------------------------------------------------------------------------------------
 // The kernel.  kCoeffs: recover and store coefficients; cost is computed when p.cost != NULL.
 // ------------------------------------------------------------------------------------------
-template <int D, bool kCoeffs>
+template <int D, bool kCoeffs, bool kGlobalSlots = false>
 __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
@@ -188,9 +232,12 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
   const int K = p.K;
   const int pos_stride = (K + 1) * D;
   const int time_stride = K;
-  double* wbase = smem + (size_t)warp * warp_smem_doubles<D>(K);
-  double* slots = wbase;                                                 // [n_slots][33]
-  double* pos_s = slots + (((size_t)lane_slots<D>(K) * kSlotStride + 1) & ~(size_t)1);   // [16][pos_stride]
+  double* wbase = smem + (size_t)warp * warp_smem_doubles<D>(K, kGlobalSlots);
+  double* slots = kGlobalSlots ? p.slot_scratch + ((size_t)blockIdx.x * warps_per_cta + warp) *
+                                                      ((size_t)lane_slots<D>(K) * kSlotStride)
+                               : wbase;                                  // [n_slots][32]
+  double* pos_s = kGlobalSlots ? wbase
+                               : slots + (((size_t)lane_slots<D>(K) * kSlotStride + 1) & ~(size_t)1);   // [16][pos_stride]
   double* time_s = pos_s + (((size_t)kPairsPerWarp * pos_stride + 1) & ~(size_t)1);      // [16][time_stride]
 
   const int side = lane & 1;   // 0: top-down lane, 1: bottom-up lane
@@ -229,7 +276,8 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
   // boundary / middle vectors during coefficient recovery)
   const int landing_slot = kF * D * mA + 2 * kF * D;
   double* landing = slots + (size_t)landing_slot * kSlotStride;
-  const bool can_prefetch = (kBlockSlots * mA - 2 * kF * D) * kSlotStride >= pos_doubles + time_doubles &&
+  const bool can_prefetch = !kGlobalSlots &&
+                            (kBlockSlots * mA - 2 * kF * D) * kSlotStride >= pos_doubles + time_doubles &&
                             ((landing_slot * kSlotStride) & 1) == 0;
   const long stride = (long)gridDim.x * pairs_per_cta;
   const long first = (long)blockIdx.x * pairs_per_cta + (long)warp * kPairsPerWarp;
@@ -334,15 +382,16 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
           // here: tp_prev = segment j-1, tp_next = segment j, S/g = reduced block j
           double* zb = my_slots + (z_off + (j - 1) * kBlockSlots) * kSlotStride;
           double* wb = my_slots + (x_off + (j - 1) * kF * D) * kSlotStride;
-          double L[10], inv[4];
-          if (!ldlt4(S, L, inv)) status |= 1;
+          double Si[10];
+          if (!spd4_inverse(S, Si)) status |= 1;
           double E[kF][kF];
           coupling_block(tp_next, E);
           double Z[kF][kF];
 #pragma unroll
           for (int b = 0; b < kF; ++b) {
-            double col[4] = {E[0][b], E[1][b], E[2][b], E[3][b]};
-            ldlt4_solve(L, inv, col);
+            const double in[4] = {E[0][b], E[1][b], E[2][b], E[3][b]};
+            double col[4];
+            sym4_apply(Si, in, col);
 #pragma unroll
             for (int a = 0; a < kF; ++a) {
               Z[a][b] = col[a];
@@ -352,8 +401,9 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
           double w[kF][D];
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            double col[4] = {g[0][d], g[1][d], g[2][d], g[3][d]};
-            ldlt4_solve(L, inv, col);
+            const double in[4] = {g[0][d], g[1][d], g[2][d], g[3][d]};
+            double col[4];
+            sym4_apply(Si, in, col);
 #pragma unroll
             for (int a = 0; a < kF; ++a) {
               w[a][d] = col[a];
@@ -495,12 +545,13 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
             const double cB = side ? c[a][d] : other;
             gm[a][d] = (gm[a][d] - cA) - cB;
           }
-        double L[10], inv[4];
-        if (!ldlt4(Sm, L, inv)) status |= 1;
+        double Si[10];
+        if (!spd4_inverse(Sm, Si)) status |= 1;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          double col[4] = {gm[0][d], gm[1][d], gm[2][d], gm[3][d]};
-          ldlt4_solve(L, inv, col);
+          const double in[4] = {gm[0][d], gm[1][d], gm[2][d], gm[3][d]};
+          double col[4];
+          sym4_apply(Si, in, col);
 #pragma unroll
           for (int a = 0; a < kF; ++a) xm[a][d] = flip[a] * col[a];   // -> local coordinates
         }
@@ -709,26 +760,34 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
 #undef H1T
 #undef A1T
 
+// Chains up to kMaxK segments keep their block storage in shared memory; longer ones (config 4,
+// K = 256) keep it in a global scratch and only stage the inputs in shared memory.
+template <int D>
+inline bool inputs_fit(int K) { return warp_smem_doubles<D>(K, true) * sizeof(double) <= kMaxDynamicSmem; }
+
 inline bool supported(int K, int D, int N, int derivative) {
-  return N == 10 && derivative == 4 && K >= 1 && K <= kMaxK && D >= 1 && D <= 3;
+  if (!(N == 10 && derivative == 4 && K >= 1 && D >= 1 && D <= 3)) return false;
+  if (K <= kMaxK) return true;
+  return D == 1 ? inputs_fit<1>(K) : D == 2 ? inputs_fit<2>(K) : inputs_fit<3>(K);
 }
 inline bool sweep_supported(int K, int D, int N, int derivative) { return supported(K, D, N, derivative); }
 
-template <int D, bool kCoeffs>
-inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
-  const size_t per_warp = warp_smem_doubles<D>(p.K) * sizeof(double);
+template <int D, bool kCoeffs, bool kGlobalSlots>
+inline cudaError_t launch_mode(FastParams p, cudaStream_t stream) {
+  const size_t per_warp = warp_smem_doubles<D>(p.K, kGlobalSlots) * sizeof(double);
   // warps per CTA that maximise resident warps per SM (shared memory is the limiter; each CTA
   // also costs 1 KB of reserved shared memory)
   int warps = 1, best = 0;
   for (int w = 1; w <= 4; ++w) {
     const size_t cta = per_warp * w + 1024;
     if (per_warp * w > kMaxDynamicSmem) break;
-    const int resident = (int)((228 * 1024) / cta) * w;
+    int resident = (int)((228 * 1024) / cta) * w;
+    if (resident > 8) resident = 8;             // 255 registers per thread: at most 8 warps per SM
     if (resident > best) { best = resident; warps = w; }
   }
   if (per_warp * warps > kMaxDynamicSmem) return cudaErrorInvalidConfiguration;
   const size_t smem = per_warp * warps;
-  auto kernel = solve_standard_pair_kernel<D, kCoeffs>;
+  auto kernel = solve_standard_pair_kernel<D, kCoeffs, kGlobalSlots>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long n_problems = p.sweep_S > 0 ? p.B * p.sweep_S : p.B;
@@ -739,8 +798,22 @@ inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
   // 4.6-batches-per-slot tail at 65,536 problems).  Very large batches loop with prefetch.
   const long max_grid = 148L * 256;
   if (grid > max_grid) grid = max_grid;
+  void* scratch = nullptr;
+  if (kGlobalSlots) {
+    const size_t bytes = (size_t)grid * warps * lane_slots<D>(p.K) * kSlotStride * sizeof(double);
+    if ((e = cudaMallocAsync(&scratch, bytes, stream)) != cudaSuccess) return e;
+    p.slot_scratch = static_cast<double*>(scratch);
+  }
   kernel<<<(int)grid, warps * 32, smem, stream>>>(p);
-  return cudaGetLastError();
+  e = cudaGetLastError();
+  if (scratch) cudaFreeAsync(scratch, stream);
+  return e;
+}
+
+template <int D, bool kCoeffs>
+inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
+  if (p.K <= kMaxK) return launch_mode<D, kCoeffs, false>(p, stream);
+  return launch_mode<D, kCoeffs, true>(p, stream);
 }
 
 inline cudaError_t launch(const StandardSolveArgs& a, cudaStream_t stream) {

@@ -250,7 +250,8 @@ def test_long_horizon_parity(ms, oracle, torch_cuda):
 # ------------------------------------------------------------------------------------------
 # standard-mask entry point (the bench path)
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("K,B", [(10, 512), (4, 64), (2, 16), (1, 8), (3, 33), (16, 40), (50, 8)])
+@pytest.mark.parametrize("K,B", [(10, 512), (4, 64), (2, 16), (1, 8), (3, 33), (16, 40), (24, 17), (25, 17), (50, 8),
+                                 (101, 5), (256, 3)])
 def test_solve_standard_against_oracle(ms, oracle, torch_cuda, K, B):
     torch = torch_cuda
     pos, times = random_batch(oracle, B, K)
