@@ -29,6 +29,8 @@
 #pragma once
 #include <cuda_pipeline.h>
 
+#include <cstdlib>
+
 #include "minsnap_device.cuh"
 #include "minsnap_launch.h"
 
@@ -44,6 +46,19 @@ constexpr int kMaxK = 24;
 
 #define H1T(r, s) (minsnap_tables::kH1_N10_d4[(r) * 10 + (s)])
 #define A1T(i, r) (minsnap_tables::kA1inv_N10[(i) * 10 + (r)])
+// coefficient store policy (measurement knob): 0 streaming (evict-first), 1 plain, 2 .cg, 3 .wt
+#ifndef MINSNAP_STORE_POLICY
+#define MINSNAP_STORE_POLICY 0
+#endif
+#if MINSNAP_STORE_POLICY == 1
+#define MINSNAP_STORE2(ptr, val) (*(ptr) = (val))
+#elif MINSNAP_STORE_POLICY == 2
+#define MINSNAP_STORE2(ptr, val) __stcg(ptr, val)
+#elif MINSNAP_STORE_POLICY == 3
+#define MINSNAP_STORE2(ptr, val) __stwt(ptr, val)
+#else
+#define MINSNAP_STORE2(ptr, val) __stcs(ptr, val)
+#endif
 
 // 1/x for a positive normal double: hardware seed (~20 bits) + two Newton steps.
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -193,8 +208,12 @@ struct FastParams {
 template <int D>
 __host__ __device__ inline int lane_slots(int K) {
   const int mA = (K - 1) / 2;
-  const int a = (kBlockSlots + kF * D) * mA;   // per eliminated block: Z (16) + w/x (4 D)
-  const int b = kF * D * mA + 2 * kF * D;      // x area + boundary and middle vectors (recovery phase)
+  // The last eliminated block of a lane stays in registers; every other block stores Z (16)
+  // and w/x (4 D).  During coefficient recovery the (dead) Z area holds three more vectors:
+  // the boundary, the middle and the last block's x.
+  const int stored = mA > 0 ? mA - 1 : 0;
+  const int a = (kBlockSlots + kF * D) * stored;
+  const int b = kF * D * stored + 3 * kF * D;
   return a > b ? a : b;
 }
 
@@ -247,7 +266,8 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
   const int nB = nb - mA - 1;  // blocks eliminated bottom-up
   const int my_n = side ? nB : mA;
   const int x_off = 0;                   // slot of w/x of block j (1-based): x_off + (j-1) * kF * D
-  const int z_off = kF * D * mA;         // slot of Z of block j: z_off + (j-1) * 16; also coefficient staging
+  const int n_stored = mA > 0 ? mA - 1 : 0;   // blocks whose Z / w live in slots (the last one stays in registers)
+  const int z_off = kF * D * n_stored;   // slot of Z of block j: z_off + (j-1) * 16
   const double flip[kF] = {side ? -1.0 : 1.0, 1.0, side ? -1.0 : 1.0, 1.0};  // (-1)^k, k = 1..4, for lane 1
 
   const long n_problems = p.sweep_S > 0 ? p.B * p.sweep_S : p.B;
@@ -274,10 +294,10 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
   const int time_doubles = (kPairsPerWarp * K + 1) & ~1;
   // landing zone of the prefetch: the Z area minus its first 2*kF*D slots (those hold the
   // boundary / middle vectors during coefficient recovery)
-  const int landing_slot = kF * D * mA + 2 * kF * D;
+  const int landing_slot = kF * D * n_stored + 3 * kF * D;
   double* landing = slots + (size_t)landing_slot * kSlotStride;
   const bool can_prefetch = !kGlobalSlots &&
-                            (kBlockSlots * mA - 2 * kF * D) * kSlotStride >= pos_doubles + time_doubles &&
+                            (kBlockSlots * n_stored - 3 * kF * D) * kSlotStride >= pos_doubles + time_doubles &&
                             ((landing_slot * kSlotStride) & 1) == 0;
   const long stride = (long)gridDim.x * pairs_per_cta;
   const long first = (long)blockIdx.x * pairs_per_cta + (long)warp * kPairsPerWarp;
@@ -338,6 +358,14 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
     auto bd = [&](int a, int d) { return bd_src ? flip[a] * bd_src[a * D + d] : 0.0; };
 
     double xm[kF][D];   // middle block solution, local coordinates
+    double Z[kF][kF], w[kF][D];   // after the forward sweep: the lane's LAST block, never written to slots
+#pragma unroll
+    for (int a = 0; a < kF; ++a) {
+#pragma unroll
+      for (int b = 0; b < kF; ++b) Z[a][b] = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) w[a][d] = 0.0;
+    }
     TimePowers tp_prev, tp_next;
     double dp_prev[D], dp_next[D];
     if (nb > 0) {
@@ -386,31 +414,30 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
           if (!spd4_inverse(S, Si)) status |= 1;
           double E[kF][kF];
           coupling_block(tp_next, E);
-          double Z[kF][kF];
 #pragma unroll
           for (int b = 0; b < kF; ++b) {
             const double in[4] = {E[0][b], E[1][b], E[2][b], E[3][b]};
             double col[4];
             sym4_apply(Si, in, col);
 #pragma unroll
-            for (int a = 0; a < kF; ++a) {
-              Z[a][b] = col[a];
-              zb[(a * kF + b) * kSlotStride] = col[a];
-            }
+            for (int a = 0; a < kF; ++a) Z[a][b] = col[a];
           }
-          double w[kF][D];
 #pragma unroll
           for (int d = 0; d < D; ++d) {
             const double in[4] = {g[0][d], g[1][d], g[2][d], g[3][d]};
             double col[4];
             sym4_apply(Si, in, col);
 #pragma unroll
-            for (int a = 0; a < kF; ++a) {
-              w[a][d] = col[a];
-              wb[(a * D + d) * kSlotStride] = col[a];
-            }
+            for (int a = 0; a < kF; ++a) w[a][d] = col[a];
           }
           if (j < my_n) {
+#pragma unroll
+            for (int a = 0; a < kF; ++a) {
+#pragma unroll
+              for (int b = 0; b < kF; ++b) zb[(a * kF + b) * kSlotStride] = Z[a][b];
+#pragma unroll
+              for (int d = 0; d < D; ++d) wb[(a * D + d) * kSlotStride] = w[a][d];
+            }
             // advance to block j+1: D_{j+1} - E^T Z,  b_{j+1} - E^T w
             tp_prev = tp_next;
             tp_next.set(local_T(j + 1));
@@ -453,25 +480,17 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
 #pragma unroll
         for (int d = 0; d < D; ++d) c[a][d] = 0.0;
       if (my_n >= 1) {
-        const double* zb = my_slots + (z_off + (my_n - 1) * kBlockSlots) * kSlotStride;
-        const double* wb = my_slots + (x_off + (my_n - 1) * kF * D) * kSlotStride;
         double E[kF][kF];
         coupling_block(tp_next, E);
 #pragma unroll
-        for (int r = 0; r < kF; ++r) {
-          double zr[kF], wr[D];
-#pragma unroll
-          for (int b = 0; b < kF; ++b) zr[b] = zb[(r * kF + b) * kSlotStride];
-#pragma unroll
-          for (int d = 0; d < D; ++d) wr[d] = wb[(r * D + d) * kSlotStride];
+        for (int r = 0; r < kF; ++r)
 #pragma unroll
           for (int a = 0; a < kF; ++a) {
 #pragma unroll
-            for (int b = 0; b <= a; ++b) C[tri(a, b)] = fma(E[r][a], zr[b], C[tri(a, b)]);
+            for (int b = 0; b <= a; ++b) C[tri(a, b)] = fma(E[r][a], Z[r][b], C[tri(a, b)]);
 #pragma unroll
-            for (int d = 0; d < D; ++d) c[a][d] = fma(E[r][a], wr[d], c[a][d]);
+            for (int d = 0; d < D; ++d) c[a][d] = fma(E[r][a], w[r][d], c[a][d]);
           }
-        }
       }
 
       // ---- middle block, solved by both lanes in the coordinates of the top-down lane -------
@@ -581,6 +600,11 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
     }
 
     // ---- back substitution outwards: x_j = w_j - Z_j x_{j+1}, stored over w_j ----------------
+    double xl[kF][D];   // x of the lane's last block (from the register copy of Z, w), local coordinates
+#pragma unroll
+    for (int a = 0; a < kF; ++a)
+#pragma unroll
+      for (int d = 0; d < D; ++d) xl[a][d] = 0.0;
     if (nb > 0) {
       double x_far[kF][D];
 #pragma unroll
@@ -591,29 +615,45 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
         const int jj = side ? j - (mA - nB) : j;
         if (jj >= 1) {
           double x_near[kF][D];
+          if (jj == my_n) {
+            // the lane's last block: Z and w never left the registers
 #pragma unroll
-          for (int a = 0; a < kF; ++a) {
-            double zrow[kF];
+            for (int a = 0; a < kF; ++a)
 #pragma unroll
-            for (int b = 0; b < kF; ++b)
-              zrow[b] = my_slots[(z_off + (jj - 1) * kBlockSlots + a * kF + b) * kSlotStride];
+              for (int d = 0; d < D; ++d) {
+                double acc = w[a][d];
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-              double acc = my_slots[(x_off + (jj - 1) * kF * D + a * D + d) * kSlotStride];
+                for (int b = 0; b < kF; ++b) acc = fma(-Z[a][b], x_far[b][d], acc);
+                x_near[a][d] = acc;
+                xl[a][d] = acc;
+              }
+          } else {
+            const double* zb = my_slots + (z_off + (jj - 1) * kBlockSlots) * kSlotStride;
+            double* wb = my_slots + (x_off + (jj - 1) * kF * D) * kSlotStride;
 #pragma unroll
-              for (int b = 0; b < kF; ++b) acc = fma(-zrow[b], x_far[b][d], acc);
-              x_near[a][d] = acc;
+            for (int a = 0; a < kF; ++a) {
+              double zrow[kF];
+#pragma unroll
+              for (int b = 0; b < kF; ++b) zrow[b] = zb[(a * kF + b) * kSlotStride];
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                double acc = wb[(a * D + d) * kSlotStride];
+#pragma unroll
+                for (int b = 0; b < kF; ++b) acc = fma(-zrow[b], x_far[b][d], acc);
+                x_near[a][d] = acc;
+              }
             }
+            // x is stored in ACTUAL coordinates (odd derivatives of the bottom-up lane flipped)
+            // so that the recovery below reads start / end vectors without any sign logic
+#pragma unroll
+            for (int a = 0; a < kF; ++a)
+#pragma unroll
+              for (int d = 0; d < D; ++d) wb[(a * D + d) * kSlotStride] = flip[a] * x_near[a][d];
           }
-          // x is stored in ACTUAL coordinates (odd derivatives of the bottom-up lane flipped)
-          // so that the recovery below reads start / end vectors without any sign logic
 #pragma unroll
           for (int a = 0; a < kF; ++a)
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-              my_slots[(x_off + (jj - 1) * kF * D + a * D + d) * kSlotStride] = flip[a] * x_near[a][d];
-              x_far[a][d] = x_near[a][d];
-            }
+            for (int d = 0; d < D; ++d) x_far[a][d] = x_near[a][d];
           if (p.free_out && active && p.sweep_S == 0) {
             const int v = side ? K - jj : jj;    // actual vertex
             double* dst = p.free_out + (prob * (long)nb + (v - 1)) * (kF * D);
@@ -625,15 +665,16 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
         }
       }
     }
-    // boundary and middle vectors (actual coordinates) join the x's in shared memory, in two
-    // groups of the now dead Z area, so every end-point vector is read the same way
-    const int bd_slot = z_off, xm_slot = z_off + kF * D;
+    // boundary, middle and last-block vectors (actual coordinates) join the x's in three groups of
+    // the now dead Z area, so every end-point vector is read the same way
+    const int bd_slot = z_off, xm_slot = z_off + kF * D, xl_slot = z_off + 2 * kF * D;
 #pragma unroll
     for (int a = 0; a < kF; ++a)
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         my_slots[(bd_slot + a * D + d) * kSlotStride] = bd_src ? bd_src[a * D + d] : 0.0;
         my_slots[(xm_slot + a * D + d) * kSlotStride] = flip[a] * xm[a][d];
+        my_slots[(xl_slot + a * D + d) * kSlotStride] = flip[a] * xl[a][d];
       }
     __syncwarp();   // all Z blocks are dead from here on: their slots receive the next batch's inputs
     if (n_next > 0 && can_prefetch) {
@@ -656,8 +697,9 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
       // end-point vectors of the segment in ACTUAL orientation (start = lower vertex index): the
       // vector of local vertex v lives at slot group  v == 0 ? boundary : v <= my_n ? x_v : middle
       const int jc = jj >= 0 ? jj : 0;
-      const int near_slot = jc >= 1 ? x_off + (jc - 1) * kF * D : bd_slot;
-      const int far_slot = jc + 1 <= my_n ? x_off + jc * kF * D : xm_slot;
+      //   v == 0 ? boundary : v < my_n ? x_v : v == my_n ? last block : middle
+      const int near_slot = jc == 0 ? bd_slot : (jc < my_n ? x_off + (jc - 1) * kF * D : xl_slot);
+      const int far_slot = jc + 1 < my_n ? x_off + jc * kF * D : (jc + 1 == my_n ? xl_slot : xm_slot);
       const double* start_ptr = my_slots + (side ? far_slot : near_slot) * kSlotStride;
       const double* end_ptr = my_slots + (side ? near_slot : far_slot) * kSlotStride;
       const int seg = side ? K - 1 - jc : jc;
@@ -710,7 +752,7 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
             double* dst = p.coeffs + ((prob * K + seg) * D + d) * kN;
             if (p.aligned16) {
 #pragma unroll
-              for (int i = 0; i < kN; i += 2) __stcs(reinterpret_cast<double2*>(dst + i), make_double2(cf[i], cf[i + 1]));
+              for (int i = 0; i < kN; i += 2) MINSNAP_STORE2(reinterpret_cast<double2*>(dst + i), make_double2(cf[i], cf[i + 1]));
             } else {
 #pragma unroll
               for (int i = 0; i < kN; ++i) __stcs(dst + i, cf[i]);
@@ -786,7 +828,20 @@ inline cudaError_t launch_mode(FastParams p, cudaStream_t stream) {
     if (resident > best) { best = resident; warps = w; }
   }
   if (per_warp * warps > kMaxDynamicSmem) return cudaErrorInvalidConfiguration;
-  const size_t smem = per_warp * warps;
+  size_t smem = per_warp * warps;
+  // Resident warps per SM.  Measured on B200 (65,536 x K=10): the cost-only kernel keeps scaling up to
+  // the register limit of 8 warps, the coefficient-writing kernel is fastest at 6-7 (its per-lane
+  // 16-byte stores and the shrunken L1 make 8 slower), so that one is padded down to 7.
+  // MINSNAP_TUNE_MAX_WARPS overrides for measurements.
+  int cap = kCoeffs ? 7 : 8;
+  if (const char* v = std::getenv("MINSNAP_TUNE_MAX_WARPS")) {
+    const int want = std::atoi(v);
+    if (want >= 1) cap = want;
+  }
+  if (warps == 1 && cap < 8) {
+    const size_t need = ((228 * 1024) / (size_t)cap - 1024) & ~(size_t)15;
+    if (need > smem && need <= kMaxDynamicSmem && (228 * 1024) / (need + 1024) == (size_t)cap) smem = need;
+  }
   auto kernel = solve_standard_pair_kernel<D, kCoeffs, kGlobalSlots>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
