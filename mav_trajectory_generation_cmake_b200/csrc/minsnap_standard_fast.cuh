@@ -856,6 +856,13 @@ inline cudaError_t launch_mode(FastParams p, cudaStream_t stream) {
   void* scratch = nullptr;
   if (kGlobalSlots) {
     const size_t bytes = (size_t)grid * warps * lane_slots<D>(p.K) * kSlotStride * sizeof(double);
+    // keep the scratch in the device's stream-ordered pool between calls (no cudaMalloc per launch)
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t threshold = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
     if ((e = cudaMallocAsync(&scratch, bytes, stream)) != cudaSuccess) return e;
     p.slot_scratch = static_cast<double*>(scratch);
   }
