@@ -174,12 +174,13 @@ static int general_common(bool solve, long B, int K, int D, int N, int derivativ
                           const double* d_fixed_values, const double* d_free_in, const double* d_times,
                           double* d_coeffs, double* d_free_out, double* d_cost, int32_t* d_status,
                           int32_t* d_col_of_row, void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
-  if (!shape_ok(B, K, D, N, derivative) || !h_fixed_mask || !d_times || !d_coeffs) return MINSNAP_ERR_ARG;
+  if (!shape_ok(B, K, D, N, derivative) || !h_fixed_mask) return MINSNAP_ERR_ARG;
+  if (B > 0 && (!d_times || !d_coeffs)) return MINSNAP_ERR_ARG;
   if (!d_workspace || workspace_bytes < SolveWorkspace::bytes(N, K)) return MINSNAP_ERR_WORKSPACE;
   int n_fixed, n_free;
   count_mask(h_fixed_mask, N, K, &n_fixed, &n_free);
-  if (n_fixed > 0 && !d_fixed_values) return MINSNAP_ERR_ARG;
-  if (!solve && n_free > 0 && !d_free_in) return MINSNAP_ERR_ARG;
+  if (B > 0 && n_fixed > 0 && !d_fixed_values) return MINSNAP_ERR_ARG;
+  if (B > 0 && !solve && n_free > 0 && !d_free_in) return MINSNAP_ERR_ARG;
   SolveWorkspace ws(d_workspace, N, K);
   CU(cudaMemcpyAsync(ws.mask, h_fixed_mask, (size_t)(K + 1) * (N / 2), cudaMemcpyHostToDevice, stream));
   CU(minsnap::launch_reorder(N, K, 1, ws.mask, ws.col_of_row, ws.counts, stream));
@@ -215,7 +216,9 @@ int minsnap_coeffs_from_constraints(long B, int K, int D, int N, const uint8_t* 
 
 int minsnap_cost(long B, int K, int D, int N, int derivative, const double* d_coeffs, const double* d_times,
                  double* d_cost, minsnap_stream_t stream) {
-  if (!shape_ok(B, K, D, N, derivative) || !d_coeffs || !d_times || !d_cost) return MINSNAP_ERR_ARG;
+  if (!shape_ok(B, K, D, N, derivative)) return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  if (!d_coeffs || !d_times || !d_cost) return MINSNAP_ERR_ARG;
   CU(minsnap::launch_cost(B, K, D, N, derivative, d_coeffs, d_times, d_cost, as_stream(stream)));
   return MINSNAP_OK;
 }
@@ -224,7 +227,9 @@ int minsnap_solve_standard(long B, int K, int D, int N, int derivative, const do
                            const double* d_end_derivatives, const double* d_times, double v_max, double a_max,
                            double magic, double* d_times_out, double* d_coeffs, double* d_free_values,
                            double* d_cost, int32_t* d_status, minsnap_stream_t stream) {
-  if (!shape_ok(B, K, D, N, derivative) || !d_positions || !d_coeffs) return MINSNAP_ERR_ARG;
+  if (!shape_ok(B, K, D, N, derivative)) return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;   // empty batch: nothing to read or write
+  if (!d_positions || !d_coeffs) return MINSNAP_ERR_ARG;
   if (!d_times && !(v_max > 0.0 && a_max > 0.0)) return MINSNAP_ERR_ARG;
   minsnap::StandardSolveArgs a;
   a.B = B; a.K = K; a.D = D; a.N = N; a.derivative = derivative;
@@ -237,9 +242,9 @@ int minsnap_solve_standard(long B, int K, int D, int N, int derivative, const do
 
 int minsnap_sample_uniform(long B, int K, int D, int N, const double* d_coeffs, const double* d_times, int M,
                            int n_deriv, double* d_out, double* d_t_out, minsnap_stream_t stream) {
-  if (B < 0 || K < 1 || D < 1 || !minsnap::supported_n(N) || M < 0 || n_deriv < 1 || !d_coeffs || !d_times ||
-      !d_out)
-    return MINSNAP_ERR_ARG;
+  if (B < 0 || K < 1 || D < 1 || !minsnap::supported_n(N) || M < 0 || n_deriv < 1) return MINSNAP_ERR_ARG;
+  if (B == 0 || M == 0) return MINSNAP_OK;
+  if (!d_coeffs || !d_times || !d_out) return MINSNAP_ERR_ARG;
   minsnap::SampleArgs a;
   a.B = B; a.K = K; a.D = D; a.N = N; a.M = M; a.n_deriv = n_deriv;
   a.d_coeffs = d_coeffs; a.d_times = d_times; a.d_t = nullptr; a.t_stride = 0;
@@ -251,9 +256,10 @@ int minsnap_sample_uniform(long B, int K, int D, int N, const double* d_coeffs, 
 int minsnap_sample_at(long B, int K, int D, int N, const double* d_coeffs, const double* d_times, int M,
                       const double* d_t, long t_stride, int n_deriv, double* d_out, int32_t* d_segment,
                       minsnap_stream_t stream) {
-  if (B < 0 || K < 1 || D < 1 || !minsnap::supported_n(N) || M < 0 || n_deriv < 1 || !d_coeffs || !d_times ||
-      !d_t || !d_out || (t_stride != 0 && t_stride < M))
+  if (B < 0 || K < 1 || D < 1 || !minsnap::supported_n(N) || M < 0 || n_deriv < 1 || (t_stride != 0 && t_stride < M))
     return MINSNAP_ERR_ARG;
+  if (B == 0 || M == 0) return MINSNAP_OK;
+  if (!d_coeffs || !d_times || !d_t || !d_out) return MINSNAP_ERR_ARG;
   minsnap::SampleArgs a;
   a.B = B; a.K = K; a.D = D; a.N = N; a.M = M; a.n_deriv = n_deriv;
   a.d_coeffs = d_coeffs; a.d_times = d_times; a.d_t = d_t; a.t_stride = t_stride;
@@ -440,9 +446,10 @@ int minsnap_solve_standard_host(long B, int K, int D, int N, int derivative, con
                                 const double* h_end_derivatives, const double* h_times, double v_max,
                                 double a_max, double magic, double* h_times_out, double* h_coeffs,
                                 double* h_free_values, double* h_cost, int32_t* h_status) {
-  if (!shape_ok(B, K, D, N, derivative) || !h_positions || !h_coeffs) return MINSNAP_ERR_ARG;
-  if (!h_times && !(v_max > 0.0 && a_max > 0.0)) return MINSNAP_ERR_ARG;
+  if (!shape_ok(B, K, D, N, derivative)) return MINSNAP_ERR_ARG;
   if (B == 0) return MINSNAP_OK;
+  if (!h_positions || !h_coeffs) return MINSNAP_ERR_ARG;
+  if (!h_times && !(v_max > 0.0 && a_max > 0.0)) return MINSNAP_ERR_ARG;
   retain_pool_memory();
   const int h = N / 2;
   const int n_free = (K - 1) * (h - 1);

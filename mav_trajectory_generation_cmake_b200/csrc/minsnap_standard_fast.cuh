@@ -19,13 +19,16 @@
 // LIN.i:252-273) of its half of the segments as soon as both end-point derivative vectors of a
 // segment are known, through  c_i = T^-i sum_r A1inv[i][r] T^(k_r) d_r .
 //
-// Per block, per lane:  S = L D L^T (no square roots), Z = S^-1 SE, w = S^-1 g are kept in
-// shared memory ([slot][lane], stride 33 doubles: conflict-free both per-lane and transposed);
+// Per block, per lane:  S^-1 explicitly through the 2x2 Schur blocks of the 4x4 SPD matrix (two
+// reciprocals, shallow dependency depth), then Z = S^-1 SE and w = S^-1 g as mat-vec products
+// (28 independent 4-FMA chains).  Z (16) and w -> x (4 D) of every eliminated block except the
+// lane's last one (that stays in registers) live in shared memory as [slot][lane] rows of 256
+// bytes (conflict-free); chains longer than kMaxK keep the same rows in a global scratch.
 // Schur update S' = D' - SE^T Z, g' = b' - SE^T w;  back substitution x = w - Z x_next.
 //
-// HBM traffic is the algorithmic minimum: positions and times are read once with coalesced
-// warp-wide loads into shared memory, coefficients are transposed through shared memory and
-// written as full 16-byte-per-lane coalesced stores.
+// HBM traffic is the algorithmic minimum: positions and times are read once (cp.async, all
+// chunks in flight before the single wait), every polynomial is written once as 80 contiguous
+// bytes with 16-byte streaming stores straight from registers.
 #pragma once
 #include <cuda_pipeline.h>
 

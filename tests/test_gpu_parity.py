@@ -486,3 +486,85 @@ def test_cost_sweep_against_oracle(ms, oracle, torch_cuda):
 def test_fp64_peak_is_plausible(ms, torch_cuda):
     tf = ms.fp64_peak(3)
     assert 5.0 < tf < 100.0
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases of the batched entry points: ragged batch sizes, empty batch, unaligned buffers, D
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 2, 15, 16, 17, 31, 33, 100])
+def test_solve_standard_ragged_batches(ms, oracle, torch_cuda, B):
+    torch = torch_cuda
+    K = 10
+    pos, times = random_batch(oracle, B, K, seed=500 + B)
+    out = ms.solve_standard(dev(torch, pos), dev(torch, times), want_cost=True)
+    ref = oracle_solve_batch(oracle, standard_mask(K), batch_values(pos), times)
+    assert out["coeffs"].shape == (B, K, 3, N)
+    assert coeff_rel_err(out["coeffs"].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
+    assert np.abs(out["cost"].cpu().numpy() / ref["cost"] - 1.0).max() <= COST_TOL
+    assert (out["status"].cpu().numpy() == 0).all()
+
+
+def test_empty_batches_are_no_ops(ms, torch_cuda):
+    torch = torch_cuda
+    pos = torch.empty((0, 11, 3), dtype=torch.float64, device="cuda")
+    times = torch.empty((0, 10), dtype=torch.float64, device="cuda")
+    out = ms.solve_standard(pos, times)
+    assert out["coeffs"].shape == (0, 10, 3, 10)
+    smp = ms.sample_uniform(out["coeffs"], times, 16, 5)
+    assert smp.shape == (0, 16, 5, 3)
+    host = ms.solve_standard_host(np.zeros((0, 11, 3)), np.zeros((0, 10)))
+    assert host["coeffs"].shape == (0, 10, 3, 10)
+
+
+def test_unaligned_device_buffers(ms, oracle, torch_cuda):
+    """Pointers that are only 8-byte aligned take the 8-byte copy / store paths."""
+    torch = torch_cuda
+    K, B = 10, 40
+    pos, times = random_batch(oracle, B, K, seed=900)
+    pos_buf = torch.empty(pos.size + 1, dtype=torch.float64, device="cuda")
+    tim_buf = torch.empty(times.size + 1, dtype=torch.float64, device="cuda")
+    out_buf = torch.empty(B * K * 3 * N + 1, dtype=torch.float64, device="cuda")
+    pos_d = pos_buf[1:].view(B, K + 1, 3)
+    tim_d = tim_buf[1:].view(B, K)
+    coeffs_d = out_buf[1:].view(B, K, 3, N)
+    pos_d.copy_(torch.from_numpy(pos))
+    tim_d.copy_(torch.from_numpy(times))
+    assert pos_d.data_ptr() % 16 == 8 and coeffs_d.data_ptr() % 16 == 8
+    ms.solve_standard(pos_d, tim_d, coeffs=coeffs_d)
+    ref = oracle_solve_batch(oracle, standard_mask(K), batch_values(pos), times)
+    assert coeff_rel_err(coeffs_d.cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
+    smp_buf = torch.empty(B * 64 * 15 + 1, dtype=torch.float64, device="cuda")
+    smp = smp_buf[1:].view(B, 64, 5, 3)
+    ms.sample_uniform(coeffs_d.contiguous(), tim_d.contiguous(), 64, 5, out=smp)
+    aligned = ms.sample_uniform(coeffs_d.contiguous(), tim_d.contiguous(), 64, 5)
+    assert torch.equal(smp, aligned)
+
+
+@pytest.mark.parametrize("D", [1, 2])
+def test_solve_standard_other_dimensions(ms, oracle, torch_cuda, D):
+    torch = torch_cuda
+    K, B = 10, 50
+    pos, times = random_batch(oracle, B, K, D, seed=40 + D)
+    out = ms.solve_standard(dev(torch, pos), dev(torch, times), want_free=True, want_cost=True)
+    ref = oracle_solve_batch(oracle, standard_mask(K), batch_values(pos), times)
+    assert coeff_rel_err(out["coeffs"].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
+    assert np.abs(out["cost"].cpu().numpy() / ref["cost"] - 1.0).max() <= COST_TOL
+    want = np.transpose(ref["d_free"], (0, 2, 1))
+    scale = np.abs(want).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(out["free_values"].cpu().numpy() - want) / scale).max() <= 1e-8
+
+
+def test_warp_specialised_variant_parity(ms, oracle, torch_cuda, monkeypatch):
+    """The opt-in warp-specialised kernel solves the same problems to the same tolerance."""
+    torch = torch_cuda
+    K, B = 10, 200
+    pos, times = random_batch(oracle, B, K, seed=321)
+    monkeypatch.setenv("MINSNAP_STANDARD_KERNEL", "ws")
+    out = ms.solve_standard(dev(torch, pos), dev(torch, times), want_cost=True, want_free=True)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("MINSNAP_STANDARD_KERNEL")
+    pair = ms.solve_standard(dev(torch, pos), dev(torch, times), want_cost=True, want_free=True)
+    ref = oracle_solve_batch(oracle, standard_mask(K), batch_values(pos), times)
+    assert coeff_rel_err(out["coeffs"].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
+    assert coeff_rel_err(out["coeffs"].cpu().numpy(), pair["coeffs"].cpu().numpy()) <= 1e-9
+    assert np.abs(out["cost"].cpu().numpy() / ref["cost"] - 1.0).max() <= COST_TOL
