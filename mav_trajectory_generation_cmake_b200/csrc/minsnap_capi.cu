@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -453,7 +454,13 @@ int minsnap_solve_standard_host(long B, int K, int D, int N, int derivative, con
   retain_pool_memory();
   const int h = N / 2;
   const int n_free = (K - 1) * (h - 1);
-  const long chunk = std::min<long>(B, 16384);
+  // chunk = unit of the copy/solve/copy pipeline (MINSNAP_TUNE_HOST_CHUNK overrides for measurements)
+  long chunk_pref = 4096;   // measured on B200 + PCIe Gen5: 4096-8192 is best (D2H stays busy, small pipeline fill)
+  if (const char* v = std::getenv("MINSNAP_TUNE_HOST_CHUNK")) {
+    const long want = std::atol(v);
+    if (want >= 16) chunk_pref = want;
+  }
+  const long chunk = std::min<long>(B, chunk_pref);
   StreamPair sp;
   CU(sp.create());
   int rc = MINSNAP_OK;
