@@ -106,6 +106,109 @@ struct StreamPair {
   }
 };
 
+
+// ---------------------------------------------------------------------------------------
+// Small host calls (one trajectory from the C++ drop-in classes): a thread-local staging arena
+// -- one pinned host block and one device block of equal size, grown on demand, released when
+// the thread exits -- turns a call into: pack inputs -> ONE H2D copy -> kernels -> ONE D2H copy
+// -> unpack.  No cudaMalloc, no stream creation, no pageable-memory copies on the way.
+// (The only state kept between calls is this cache of CUDA resources, private to the thread.)
+// ---------------------------------------------------------------------------------------
+constexpr size_t kSmallCallBytes = 4u << 20;
+
+struct HostArena {
+  char* h = nullptr;
+  char* d = nullptr;
+  size_t cap = 0;
+  int device = -1;
+  ~HostArena() { release(); }
+  void release() {
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
+    h = d = nullptr;
+    cap = 0;
+  }
+  cudaError_t ensure(size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev == device && bytes <= cap) return cudaSuccess;
+    release();
+    size_t want = 64u << 10;
+    while (want < bytes) want <<= 1;
+    if ((e = cudaHostAlloc(reinterpret_cast<void**>(&h), want, cudaHostAllocDefault)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&d), want)) != cudaSuccess) return e;
+    cap = want;
+    device = dev;
+    return cudaSuccess;
+  }
+};
+thread_local HostArena g_arena;
+
+class SmallCall {
+ public:
+  explicit SmallCall(cudaStream_t st) : st_(st) {}
+  // declare buffers first (inputs, outputs, device-only scratch), then upload()
+  int in(const void* src, size_t bytes) { return add(ins_, const_cast<void*>(src), bytes); }
+  int out(void* dst, size_t bytes) { return add(outs_, dst, bytes) + 1000; }
+  int scratch(size_t bytes) { return add(tmps_, nullptr, bytes) + 2000; }
+  size_t total_bytes() const { return sum(ins_) + sum(outs_) + sum(tmps_); }
+  cudaError_t upload() {
+    size_t off = 0;
+    for (auto& b : ins_) { b.off = off; off += pad(b.bytes); }
+    in_end_ = off;
+    for (auto& b : outs_) { b.off = off; off += pad(b.bytes); }
+    out_end_ = off;
+    for (auto& b : tmps_) { b.off = off; off += pad(b.bytes); }
+    cudaError_t e = g_arena.ensure(off ? off : 16);
+    if (e != cudaSuccess) return e;
+    for (auto& b : ins_)
+      if (b.host && b.bytes) std::memcpy(g_arena.h + b.off, b.host, b.bytes);
+    if (in_end_ == 0) return cudaSuccess;
+    return cudaMemcpyAsync(g_arena.d, g_arena.h, in_end_, cudaMemcpyHostToDevice, st_);
+  }
+  template <typename T>
+  T* dev(int id) const {
+    const Buf& b = id >= 2000 ? tmps_[id - 2000] : id >= 1000 ? outs_[id - 1000] : ins_[id];
+    return reinterpret_cast<T*>(g_arena.d + b.off);
+  }
+  template <typename T>
+  const T* host(int id) const {
+    const Buf& b = id >= 2000 ? tmps_[id - 2000] : id >= 1000 ? outs_[id - 1000] : ins_[id];
+    return reinterpret_cast<const T*>(g_arena.h + b.off);
+  }
+  // copies every output back, waits, unpacks into the caller's buffers
+  cudaError_t download() {
+    cudaError_t e = cudaSuccess;
+    if (out_end_ > in_end_)
+      e = cudaMemcpyAsync(g_arena.h + in_end_, g_arena.d + in_end_, out_end_ - in_end_, cudaMemcpyDeviceToHost, st_);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st_)) != cudaSuccess) return e;
+    for (auto& b : outs_)
+      if (b.host && b.bytes) std::memcpy(b.host, g_arena.h + b.off, b.bytes);
+    return cudaSuccess;
+  }
+
+ private:
+  struct Buf {
+    void* host;
+    size_t bytes, off;
+  };
+  static size_t pad(size_t b) { return (b + 255) & ~size_t(255); }
+  static size_t sum(const std::vector<Buf>& v) {
+    size_t t = 0;
+    for (auto& b : v) t += pad(b.bytes);
+    return t;
+  }
+  static int add(std::vector<Buf>& v, void* host, size_t bytes) {
+    v.push_back(Buf{host, bytes, 0});
+    return static_cast<int>(v.size()) - 1;
+  }
+  cudaStream_t st_;
+  std::vector<Buf> ins_, outs_, tmps_;
+  size_t in_end_ = 0, out_end_ = 0;
+};
+
 }  // namespace
 
 extern "C" {
@@ -312,8 +415,22 @@ int minsnap_reorder_host(int N, int K, long n_masks, const uint8_t* h_mask, int3
   if (!minsnap::supported_n(N) || K < 1 || n_masks < 0 || !h_mask || !h_col_of_row || !h_counts)
     return MINSNAP_ERR_ARG;
   if (n_masks == 0) return MINSNAP_OK;
-  cudaStream_t st;
-  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  {
+    SmallCall sc(cudaStreamPerThread);
+    const size_t nm = (size_t)n_masks;
+    const int i_mask = sc.in(h_mask, nm * (K + 1) * (N / 2));
+    const int o_col = sc.out(h_col_of_row, sizeof(int32_t) * nm * N * K);
+    const int o_cnt = sc.out(h_counts, sizeof(int32_t) * nm * 2);
+    if (sc.total_bytes() <= kSmallCallBytes) {
+      CU(sc.upload());
+      const int rc = minsnap_reorder(N, K, n_masks, sc.dev<uint8_t>(i_mask), sc.dev<int32_t>(o_col),
+                                     sc.dev<int32_t>(o_cnt), cudaStreamPerThread);
+      if (rc != MINSNAP_OK) return rc;
+      CU(sc.download());
+      return MINSNAP_OK;
+    }
+  }
+  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
   int rc = MINSNAP_OK;
   {
     Scratch mk, col, cnt;
@@ -331,7 +448,6 @@ int minsnap_reorder_host(int N, int K, long n_masks, const uint8_t* h_mask, int3
   done:;
   }
   cudaError_t es = cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
   if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
   return rc;
 }
@@ -344,8 +460,31 @@ int minsnap_solve_host(long B, int K, int D, int N, int derivative, const uint8_
   count_mask(h_fixed_mask, N, K, &n_fixed, &n_free);
   if (n_fixed > 0 && !h_fixed_values) return MINSNAP_ERR_ARG;
   retain_pool_memory();
-  cudaStream_t st;
-  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  if (B == 0) return MINSNAP_OK;
+  {
+    SmallCall sc(cudaStreamPerThread);
+    const size_t nb = (size_t)B;
+    const int i_fixed = sc.in(h_fixed_values, sizeof(double) * nb * n_fixed * D);
+    const int i_times = sc.in(h_times, sizeof(double) * nb * K);
+    const int o_coeffs = sc.out(h_coeffs, sizeof(double) * nb * K * D * N);
+    const int o_free = sc.out(h_free_values, sizeof(double) * nb * n_free * D);
+    const int o_cost = sc.out(h_cost, sizeof(double) * nb);
+    const int o_status = sc.out(h_status, sizeof(int32_t) * nb);
+    const int o_col = sc.out(h_col_of_row, sizeof(int32_t) * (size_t)N * K);
+    const int t_ws = sc.scratch(SolveWorkspace::bytes(N, K));
+    if (sc.total_bytes() <= kSmallCallBytes) {
+      CU(sc.upload());
+      const int rc = minsnap_solve(B, K, D, N, derivative, h_fixed_mask, sc.dev<double>(i_fixed),
+                                   sc.dev<double>(i_times), sc.dev<double>(o_coeffs), sc.dev<double>(o_free),
+                                   h_cost ? sc.dev<double>(o_cost) : nullptr, sc.dev<int32_t>(o_status),
+                                   sc.dev<int32_t>(o_col), sc.dev<char>(t_ws), SolveWorkspace::bytes(N, K),
+                                   cudaStreamPerThread);
+      if (rc != MINSNAP_OK) return rc;
+      CU(sc.download());
+      return MINSNAP_OK;
+    }
+  }
+  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
   int rc = MINSNAP_OK;
   {
     Scratch fv, tm, co, fr, cs, ss, ws, cr;
@@ -376,7 +515,6 @@ int minsnap_solve_host(long B, int K, int D, int N, int derivative, const uint8_
   done:;
   }
   cudaError_t es = cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
   if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
   return rc;
 }
@@ -388,8 +526,27 @@ int minsnap_coeffs_from_constraints_host(long B, int K, int D, int N, const uint
   int n_fixed, n_free;
   count_mask(h_fixed_mask, N, K, &n_fixed, &n_free);
   if ((n_fixed > 0 && !h_fixed_values) || (n_free > 0 && !h_free_values)) return MINSNAP_ERR_ARG;
-  cudaStream_t st;
-  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  if (B == 0) return MINSNAP_OK;
+  {
+    SmallCall sc(cudaStreamPerThread);
+    const size_t nb = (size_t)B;
+    const int i_fixed = sc.in(h_fixed_values, sizeof(double) * nb * n_fixed * D);
+    const int i_free = sc.in(h_free_values, sizeof(double) * nb * n_free * D);
+    const int i_times = sc.in(h_times, sizeof(double) * nb * K);
+    const int o_coeffs = sc.out(h_coeffs, sizeof(double) * nb * K * D * N);
+    const int t_ws = sc.scratch(SolveWorkspace::bytes(N, K));
+    if (sc.total_bytes() <= kSmallCallBytes) {
+      CU(sc.upload());
+      const int rc = minsnap_coeffs_from_constraints(B, K, D, N, h_fixed_mask, sc.dev<double>(i_fixed),
+                                                     sc.dev<double>(i_free), sc.dev<double>(i_times),
+                                                     sc.dev<double>(o_coeffs), sc.dev<char>(t_ws),
+                                                     SolveWorkspace::bytes(N, K), cudaStreamPerThread);
+      if (rc != MINSNAP_OK) return rc;
+      CU(sc.download());
+      return MINSNAP_OK;
+    }
+  }
+  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
   int rc = MINSNAP_OK;
   {
     Scratch fv, fr, tm, co, ws;
@@ -411,7 +568,6 @@ int minsnap_coeffs_from_constraints_host(long B, int K, int D, int N, const uint
   done:;
   }
   cudaError_t es = cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
   if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
   return rc;
 }
@@ -419,8 +575,23 @@ int minsnap_coeffs_from_constraints_host(long B, int K, int D, int N, const uint
 int minsnap_cost_host(long B, int K, int D, int N, int derivative, const double* h_coeffs, const double* h_times,
                       double* h_cost) {
   if (!shape_ok(B, K, D, N, derivative) || !h_coeffs || !h_times || !h_cost) return MINSNAP_ERR_ARG;
-  cudaStream_t st;
-  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  if (B == 0) return MINSNAP_OK;
+  {
+    SmallCall sc(cudaStreamPerThread);
+    const size_t nb = (size_t)B;
+    const int i_coeffs = sc.in(h_coeffs, sizeof(double) * nb * K * D * N);
+    const int i_times = sc.in(h_times, sizeof(double) * nb * K);
+    const int o_cost = sc.out(h_cost, sizeof(double) * nb);
+    if (sc.total_bytes() <= kSmallCallBytes) {
+      CU(sc.upload());
+      const int rc = minsnap_cost(B, K, D, N, derivative, sc.dev<double>(i_coeffs), sc.dev<double>(i_times),
+                                  sc.dev<double>(o_cost), cudaStreamPerThread);
+      if (rc != MINSNAP_OK) return rc;
+      CU(sc.download());
+      return MINSNAP_OK;
+    }
+  }
+  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
   int rc = MINSNAP_OK;
   {
     Scratch co, tm, cs;
@@ -436,7 +607,6 @@ int minsnap_cost_host(long B, int K, int D, int N, int derivative, const double*
   done:;
   }
   cudaError_t es = cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
   if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
   return rc;
 }
@@ -451,6 +621,33 @@ int minsnap_solve_standard_host(long B, int K, int D, int N, int derivative, con
   if (B == 0) return MINSNAP_OK;
   if (!h_positions || !h_coeffs) return MINSNAP_ERR_ARG;
   if (!h_times && !(v_max > 0.0 && a_max > 0.0)) return MINSNAP_ERR_ARG;
+  {
+    SmallCall sc(cudaStreamPerThread);
+    const size_t nb = (size_t)B;
+    const int hh = N / 2;
+    const size_t n_free_s = (size_t)(K > 1 ? (K - 1) * (hh - 1) : 0);
+    const int i_pos = sc.in(h_positions, sizeof(double) * nb * (K + 1) * D);
+    const int i_end = sc.in(h_end_derivatives, h_end_derivatives ? sizeof(double) * nb * 2 * (hh - 1) * D : 0);
+    const int i_tm = sc.in(h_times, h_times ? sizeof(double) * nb * K : 0);
+    const int o_tm = sc.out(h_times ? nullptr : h_times_out, sizeof(double) * nb * K);
+    const int o_coeffs = sc.out(h_coeffs, sizeof(double) * nb * K * D * N);
+    const int o_free = sc.out(h_free_values, h_free_values ? sizeof(double) * nb * n_free_s * D : 0);
+    const int o_cost = sc.out(h_cost, h_cost ? sizeof(double) * nb : 0);
+    const int o_status = sc.out(h_status, h_status ? sizeof(int32_t) * nb : 0);
+    if (sc.total_bytes() <= kSmallCallBytes) {
+      CU(sc.upload());
+      const int rc = minsnap_solve_standard(
+          B, K, D, N, derivative, sc.dev<double>(i_pos), h_end_derivatives ? sc.dev<double>(i_end) : nullptr,
+          h_times ? sc.dev<double>(i_tm) : nullptr, v_max, a_max, magic,
+          (!h_times && h_times_out) ? sc.dev<double>(o_tm) : nullptr, sc.dev<double>(o_coeffs),
+          h_free_values ? sc.dev<double>(o_free) : nullptr, h_cost ? sc.dev<double>(o_cost) : nullptr,
+          h_status ? sc.dev<int32_t>(o_status) : nullptr, cudaStreamPerThread);
+      if (rc != MINSNAP_OK) return rc;
+      CU(sc.download());
+      if (h_times && h_times_out) std::memcpy(h_times_out, h_times, sizeof(double) * nb * K);
+      return MINSNAP_OK;
+    }
+  }
   retain_pool_memory();
   const int h = N / 2;
   const int n_free = (K - 1) * (h - 1);
@@ -525,8 +722,26 @@ int minsnap_sample_at_host(long B, int K, int D, int N, const double* h_coeffs, 
       !h_t || !h_out || (t_stride != 0 && t_stride < M))
     return MINSNAP_ERR_ARG;
   if (B == 0 || M == 0) return MINSNAP_OK;
-  cudaStream_t st;
-  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  {
+    SmallCall sc(cudaStreamPerThread);
+    const size_t nb = (size_t)B;
+    const size_t n_t = t_stride == 0 ? (size_t)M : nb * (size_t)t_stride;
+    const int i_coeffs = sc.in(h_coeffs, sizeof(double) * nb * K * D * N);
+    const int i_times = sc.in(h_times, sizeof(double) * nb * K);
+    const int i_t = sc.in(h_t, sizeof(double) * n_t);
+    const int o_out = sc.out(h_out, sizeof(double) * nb * M * n_deriv * D);
+    const int o_seg = sc.out(h_segment, sizeof(int32_t) * nb * M);
+    if (sc.total_bytes() <= kSmallCallBytes) {
+      CU(sc.upload());
+      const int rc = minsnap_sample_at(B, K, D, N, sc.dev<double>(i_coeffs), sc.dev<double>(i_times), M,
+                                       sc.dev<double>(i_t), t_stride, n_deriv, sc.dev<double>(o_out),
+                                       h_segment ? sc.dev<int32_t>(o_seg) : nullptr, cudaStreamPerThread);
+      if (rc != MINSNAP_OK) return rc;
+      CU(sc.download());
+      return MINSNAP_OK;
+    }
+  }
+  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
   int rc = MINSNAP_OK;
   {
     Scratch co, tm, tt, out, sg;
@@ -548,7 +763,6 @@ int minsnap_sample_at_host(long B, int K, int D, int N, const double* h_coeffs, 
   done:;
   }
   cudaError_t es = cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
   if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
   return rc;
 }
@@ -559,8 +773,28 @@ int minsnap_evaluate_range_host(int K, int D, int N, const double* h_coeffs, con
   if (K < 1 || D < 1 || !minsnap::supported_n(N) || !(dt > 0.0) || derivative < 0 || max_samples < 0 || !h_coeffs ||
       !h_times || !h_out || !h_count)
     return MINSNAP_ERR_ARG;
-  cudaStream_t st;
-  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  {
+    SmallCall sc(cudaStreamPerThread);
+    const int i_coeffs = sc.in(h_coeffs, sizeof(double) * (size_t)K * D * N);
+    const int i_times = sc.in(h_times, sizeof(double) * (size_t)K);
+    const int o_out = sc.out(nullptr, sizeof(double) * (size_t)max_samples * D);
+    const int o_t = sc.out(nullptr, sizeof(double) * (size_t)max_samples);
+    const int o_cnt = sc.out(h_count, sizeof(int32_t));
+    if (sc.total_bytes() <= kSmallCallBytes) {
+      CU(sc.upload());
+      const int rc = minsnap_evaluate_range(1, K, D, N, sc.dev<double>(i_coeffs), sc.dev<double>(i_times), t_start,
+                                            t_end, dt, derivative, max_samples, sc.dev<double>(o_out),
+                                            sc.dev<double>(o_t), sc.dev<int32_t>(o_cnt), cudaStreamPerThread);
+      if (rc != MINSNAP_OK) return rc;
+      CU(sc.download());
+      // only the emitted samples are meaningful: copy those out of the staging block
+      const size_t n_emit = (size_t)std::min(*h_count, max_samples);
+      std::memcpy(h_out, sc.host<double>(o_out), sizeof(double) * n_emit * D);
+      if (h_t_out) std::memcpy(h_t_out, sc.host<double>(o_t), sizeof(double) * n_emit);
+      return MINSNAP_OK;
+    }
+  }
+  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
   int rc = MINSNAP_OK;
   {
     Scratch co, tm, out, tt, cnt;
@@ -586,7 +820,6 @@ int minsnap_evaluate_range_host(int K, int D, int N, const double* h_coeffs, con
   done:;
   }
   cudaError_t es = cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
   if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
   return rc;
 }
@@ -595,8 +828,24 @@ int minsnap_segment_matrices_host(long n, int N, int derivative, const double* h
                                   double* h_Q, double* h_H) {
   if (n < 0 || !minsnap::supported_n(N) || derivative < 0 || derivative > N / 2 - 1 || !h_T) return MINSNAP_ERR_ARG;
   if (n == 0) return MINSNAP_OK;
-  cudaStream_t st;
-  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  {
+    SmallCall sc(cudaStreamPerThread);
+    const size_t mat = sizeof(double) * (size_t)n * N * N;
+    const int i_T = sc.in(h_T, sizeof(double) * (size_t)n);
+    const int o_A = sc.out(h_A, h_A ? mat : 0), o_Ai = sc.out(h_Ainv, h_Ainv ? mat : 0);
+    const int o_Q = sc.out(h_Q, h_Q ? mat : 0), o_H = sc.out(h_H, h_H ? mat : 0);
+    if (sc.total_bytes() <= kSmallCallBytes) {
+      CU(sc.upload());
+      const int rc = minsnap_segment_matrices(n, N, derivative, sc.dev<double>(i_T), h_A ? sc.dev<double>(o_A) : nullptr,
+                                              h_Ainv ? sc.dev<double>(o_Ai) : nullptr,
+                                              h_Q ? sc.dev<double>(o_Q) : nullptr, h_H ? sc.dev<double>(o_H) : nullptr,
+                                              cudaStreamPerThread);
+      if (rc != MINSNAP_OK) return rc;
+      CU(sc.download());
+      return MINSNAP_OK;
+    }
+  }
+  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
   int rc = MINSNAP_OK;
   {
     Scratch T, A, Ai, Q, H;
@@ -617,7 +866,6 @@ int minsnap_segment_matrices_host(long n, int N, int derivative, const double* h
   done:;
   }
   cudaError_t es = cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
   if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
   return rc;
 }
@@ -626,8 +874,21 @@ int minsnap_estimate_segment_times_host(long B, int K, int D, const double* h_po
                                         double a_max, double magic, double* h_times) {
   if (B < 0 || K < 1 || D < 1 || !h_positions || !h_times) return MINSNAP_ERR_ARG;
   if (B == 0) return MINSNAP_OK;
-  cudaStream_t st;
-  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  {
+    SmallCall sc(cudaStreamPerThread);
+    const size_t nb = (size_t)B;
+    const int i_pos = sc.in(h_positions, sizeof(double) * nb * (K + 1) * D);
+    const int o_times = sc.out(h_times, sizeof(double) * nb * K);
+    if (sc.total_bytes() <= kSmallCallBytes) {
+      CU(sc.upload());
+      const int rc = minsnap_estimate_segment_times(B, K, D, sc.dev<double>(i_pos), v_max, a_max, magic,
+                                                    sc.dev<double>(o_times), cudaStreamPerThread);
+      if (rc != MINSNAP_OK) return rc;
+      CU(sc.download());
+      return MINSNAP_OK;
+    }
+  }
+  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
   int rc = MINSNAP_OK;
   {
     Scratch pos, tm;
@@ -641,7 +902,6 @@ int minsnap_estimate_segment_times_host(long B, int K, int D, const double* h_po
   done:;
   }
   cudaError_t es = cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
   if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
   return rc;
 }

@@ -730,36 +730,50 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
       const double i2 = i1 * i1, i4 = i2 * i2, i5 = i4 * i1;
       if (kCoeffs) {
         const double ipow[5] = {i5, i5 * i1, i5 * i2, i4 * i4, i4 * i5};   // T^-5 .. T^-9
+        // Row-outer, dimension-inner: the 9 table constants of an output row are live only while
+        // they are applied to the D dimensions (short live ranges -> no constant-register hoarding).
+        double cf[D][kN];
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          double cf[kN];
-          cf[0] = my_pos[seg * D + d];
+        for (int d = 0; d < D; ++d) cf[d][0] = my_pos[seg * D + d];
 #pragma unroll
-          for (int a = 0; a < kF; ++a) cf[1 + a] = A1T(1 + a, 1 + a) * ds[a][d];
+        for (int a = 0; a < kF; ++a) {
+          const double ka = A1T(1 + a, 1 + a);
 #pragma unroll
-          for (int i = 5; i < kN; ++i) {
+          for (int d = 0; d < D; ++d) cf[d][1 + a] = ka * ds[a][d];
+        }
+#pragma unroll
+        for (int i = 5; i < kN; ++i) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
             double acc = A1T(i, 5) * u[0][d];
 #pragma unroll
             for (int a = 0; a < kF; ++a) {
               acc = fma(A1T(i, 1 + a), u[1 + a][d], acc);
               acc = fma(A1T(i, 6 + a), u[1 + kF + a][d], acc);
             }
-            cf[i] = acc * ipow[i - 5];
+            cf[d][i] = acc * ipow[i - 5];
           }
-          double chk = 0.0;
+        }
+        double chk = 0.0;
 #pragma unroll
-          for (int i = 0; i < kN; ++i) chk = fma(cf[i], 0.0, chk);   // NaN iff any coefficient is non-finite
-          if (chk != 0.0) nonfinite = 1;
-          if (mine) {
-            // the polynomial's 10 coefficients are 80 contiguous, 16-byte aligned bytes of HBM
-            double* dst = p.coeffs + ((prob * K + seg) * D + d) * kN;
-            if (p.aligned16) {
+        for (int d = 0; d < D; ++d)
 #pragma unroll
-              for (int i = 0; i < kN; i += 2) MINSNAP_STORE2(reinterpret_cast<double2*>(dst + i), make_double2(cf[i], cf[i + 1]));
-            } else {
+          for (int i = 0; i < kN; ++i) chk = fma(cf[d][i], 0.0, chk);   // NaN iff any coefficient is non-finite
+        if (chk != 0.0) nonfinite = 1;
+        if (mine) {
+          // the segment's D polynomials are 80 D contiguous, 16-byte aligned bytes of HBM
+          double* dst = p.coeffs + (prob * K + seg) * (D * kN);
+          if (p.aligned16) {
 #pragma unroll
-              for (int i = 0; i < kN; ++i) __stcs(dst + i, cf[i]);
-            }
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+              for (int i = 0; i < kN; i += 2)
+                MINSNAP_STORE2(reinterpret_cast<double2*>(dst + d * kN + i), make_double2(cf[d][i], cf[d][i + 1]));
+          } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+              for (int i = 0; i < kN; ++i) __stcs(dst + d * kN + i, cf[d][i]);
           }
         }
       }
