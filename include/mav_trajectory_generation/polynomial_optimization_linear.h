@@ -158,9 +158,31 @@ class PolynomialOptimization {
     std::vector<double> fixed = interleave(fixed_constraints_compact_, n_fixed_constraints_);
     std::vector<double> coeffs(static_cast<size_t>(K) * D * N), free_values(n_free_constraints_ * D);
     int32_t status = 0;
-    gpu::check(minsnap_solve_host(1, K, D, N, derivative_to_optimize_, fixed_mask_.data(), fixed.data(),
-                                  segment_times_.data(), coeffs.data(), free_values.data(), nullptr, &status, nullptr),
-               "minsnap_solve_host");
+    if (hasStandardStructure()) {
+      // createRandomVertices structure (ends fully fixed, interior position only), N = 10, snap:
+      // the single-launch kernel.  Column order of d_f: vertex 0 (derivatives 0..4), interior
+      // positions, vertex K (derivatives 0..4).
+      const int h = N / 2;
+      std::vector<double> positions(static_cast<size_t>(K + 1) * D), ends(static_cast<size_t>(2) * (h - 1) * D);
+      for (int d = 0; d < D; ++d) {
+        positions[d] = fixed[d];
+        for (int v = 1; v < K; ++v) positions[static_cast<size_t>(v) * D + d] = fixed[static_cast<size_t>(h - 1 + v) * D + d];
+        positions[static_cast<size_t>(K) * D + d] = fixed[static_cast<size_t>(h + K - 1) * D + d];
+        for (int c = 1; c < h; ++c) {
+          ends[static_cast<size_t>(c - 1) * D + d] = fixed[static_cast<size_t>(c) * D + d];
+          ends[static_cast<size_t>(h - 1 + c - 1) * D + d] = fixed[static_cast<size_t>(h + K - 1 + c) * D + d];
+        }
+      }
+      gpu::check(minsnap_solve_standard_host(1, K, D, N, derivative_to_optimize_, positions.data(), ends.data(),
+                                             segment_times_.data(), 0.0, 0.0, 0.0, nullptr, coeffs.data(),
+                                             free_values.data(), nullptr, &status),
+                 "minsnap_solve_standard_host");
+    } else {
+      gpu::check(minsnap_solve_host(1, K, D, N, derivative_to_optimize_, fixed_mask_.data(), fixed.data(),
+                                    segment_times_.data(), coeffs.data(), free_values.data(), nullptr, &status,
+                                    nullptr),
+                 "minsnap_solve_host");
+    }
     if (status != MINSNAP_STATUS_OK)
       LOG(WARNING) << "solveLinear: GPU status word " << status
                    << " (1 = R_pp not positive definite, 2 = bad segment time, 4 = non-finite coefficient)";
@@ -254,6 +276,19 @@ class PolynomialOptimization {
   }
 
  private:
+  // True for the constraint structure createRandomVertices produces (ref src/vertex.cpp:59,71-76)
+  // when the fast standard-mask entry point covers the problem (N = 10, snap, D <= 3).
+  bool hasStandardStructure() const {
+    if (N != 10 || derivative_to_optimize_ != N / 2 - 1 || dimension_ > 3 || n_segments_ < 2) return false;
+    const size_t h = N / 2;
+    for (size_t v = 0; v < n_vertices_; ++v)
+      for (size_t c = 0; c < h; ++c) {
+        const bool want = c == 0 || v == 0 || v + 1 == n_vertices_;
+        if ((fixed_mask_[v * h + c] != 0) != want) return false;
+      }
+    return true;
+  }
+
   // row-major [N][N] buffer of the C ABI -> matrix (independent of the matrix storage order)
   static void fillSquare(const double* buf, SquareMatrix* m) {
     for (int r = 0; r < N; ++r)
