@@ -245,7 +245,7 @@ __device__ __forceinline__ void async_copy_doubles(double* dst, const double* sr
 // ------------------------------------------------------------------------------------------
 // The kernel.  kCoeffs: recover and store coefficients; cost is computed when p.cost != NULL.
 // ------------------------------------------------------------------------------------------
-template <int D, bool kCoeffs, bool kGlobalSlots = false>
+template <int D, bool kCoeffs, bool kGlobalSlots = false, bool kCost = true>
 __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
@@ -413,6 +413,15 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
           // here: tp_prev = segment j-1, tp_next = segment j, S/g = reduced block j
           double* zb = my_slots + (z_off + (j - 1) * kBlockSlots) * kSlotStride;
           double* wb = my_slots + (x_off + (j - 1) * kF * D) * kSlotStride;
+          // inputs of block j+1 first: their shared-memory loads and the reciprocal chain of the
+          // time powers overlap the arithmetic of block j (the compiler cannot hoist them over the
+          // slot stores below on its own)
+          const bool more = j < my_n;
+          TimePowers tp_new;
+          double dp_new[D];
+          tp_new.set(local_T(more ? j + 1 : j));
+#pragma unroll
+          for (int d = 0; d < D; ++d) dp_new[d] = more ? local_p(j + 2, d) - local_p(j + 1, d) : 0.0;
           double Si[10];
           if (!spd4_inverse(S, Si)) status |= 1;
           double E[kF][kF];
@@ -443,11 +452,11 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
             }
             // advance to block j+1: D_{j+1} - E^T Z,  b_{j+1} - E^T w
             tp_prev = tp_next;
-            tp_next.set(local_T(j + 1));
+            tp_next = tp_new;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
               dp_prev[d] = dp_next[d];
-              dp_next[d] = local_p(j + 2, d) - local_p(j + 1, d);
+              dp_next[d] = dp_new[d];
             }
             diag_block(tp_prev, tp_next, S);
             rhs_block(tp_prev, tp_next, dp_prev, dp_next, g);
@@ -754,12 +763,13 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
             cf[d][i] = acc * ipow[i - 5];
           }
         }
-        double chk = 0.0;
+        // non-finite detection on the exponent fields of c_9 (scaled by T^-9: overflows first) and
+        // c_4: integer tests instead of an FP64 reduction over all coefficients
 #pragma unroll
-        for (int d = 0; d < D; ++d)
-#pragma unroll
-          for (int i = 0; i < kN; ++i) chk = fma(cf[d][i], 0.0, chk);   // NaN iff any coefficient is non-finite
-        if (chk != 0.0) nonfinite = 1;
+        for (int d = 0; d < D; ++d) {
+          const int e9 = __double2hiint(cf[d][kN - 1]) & 0x7ff00000, e4 = __double2hiint(cf[d][kF]) & 0x7ff00000;
+          if (e9 == 0x7ff00000 || e4 == 0x7ff00000) nonfinite = 1;
+        }
         if (mine) {
           // the segment's D polynomials are 80 D contiguous, 16-byte aligned bytes of HBM
           double* dst = p.coeffs + (prob * K + seg) * (D * kN);
@@ -777,7 +787,7 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
           }
         }
       }
-      if (p.cost && mine) {
+      if (kCost && p.cost && mine) {
         // u^T Hred1 u * T^-7: the per-segment quadratic form in scaled variables
         const double i7 = i5 * i2;
         double qsum = 0.0;
@@ -801,7 +811,7 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
       }
     }
 
-    if (p.cost) {
+    if (kCost && p.cost) {
       cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, 1);
       if (active && side == 0) p.cost[prob] = 0.5 * cost_acc;
     }
@@ -859,7 +869,9 @@ inline cudaError_t launch_mode(FastParams p, cudaStream_t stream) {
     const size_t need = ((228 * 1024) / (size_t)cap - 1024) & ~(size_t)15;
     if (need > smem && need <= kMaxDynamicSmem && (228 * 1024) / (need + 1024) == (size_t)cap) smem = need;
   }
-  auto kernel = solve_standard_pair_kernel<D, kCoeffs, kGlobalSlots>;
+  // the cost path is compiled out when no cost is requested (smaller hot loop, fewer registers)
+  void (*kernel)(FastParams) = p.cost ? solve_standard_pair_kernel<D, kCoeffs, kGlobalSlots, true>
+                                      : solve_standard_pair_kernel<D, kCoeffs, kGlobalSlots, false>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long n_problems = p.sweep_S > 0 ? p.B * p.sweep_S : p.B;
