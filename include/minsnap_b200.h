@@ -176,6 +176,40 @@ MINSNAP_API int minsnap_cost_sweep(long B, int S, int K, int D, int N, int deriv
                                    const double* d_times, double* d_cost, int32_t* d_status,
                                    minsnap_stream_t stream);
 
+/* ---- extrema of the magnitude of a derivative --------------------------------
+ * ref: PolynomialOptimization::computeMaximumOfMagnitude<Derivative> (LIN.i:470-503) with
+ *      computeSegmentMaximumMagnitudeCandidates (LIN.i:378-437)              -> mode 0
+ *      Trajectory::computeMinMaxMagnitude (src/trajectory.cpp:181-217) with
+ *      Segment::computeMinMaxMagnitudeCandidates / selectMinMaxMagnitudeFromCandidates
+ *      (src/segment.cpp:82-199)                                              -> mode 1
+ *      root finder findRootsJenkinsTraub (src/rpoly.cpp), replaced by real-root isolation.
+ * Candidate times of a segment: the real roots inside [0, T] of sum_dim p^(k) p^(k+1) (several
+ * dimensions) or of p^(k+1) (one dimension), trailing coefficients below machine epsilon removed
+ * as the reference does (src/rpoly.cpp:44-75).
+ *   mode 0 (MINSNAP_EXTREMA_OPTIMIZATION): per segment t = 0 and the roots, plus the end of the
+ *          last segment; maximum only, starting from (time 0, value 0, segment 0); d_min_* unused.
+ *   mode 1 (MINSNAP_EXTREMA_TRAJECTORY): per segment start, end and the roots; minimum and maximum.
+ * A later candidate replaces the incumbent only when strictly larger (smaller).
+ * MINSNAP_EXTREMA_KEEP_SMALL_COEFFICIENTS may be OR-ed into mode: the reference's coefficient
+ * threshold is absolute (2.2e-16), which on segments longer than about 12 s removes terms of the
+ * candidate polynomial that matter near the end of the segment, so the reference (and this
+ * function by default, for parity) can miss extrema there; with the flag only exact zeros are
+ * removed and the result agrees with dense sampling.
+ * dim_mask: bit d set => dimension d takes part; 0 => all D dimensions (D <= 32).
+ * Times are relative to the start of the reported segment, as in the reference's Extremum.
+ * Outputs [B] each, any may be NULL.  Optional d_root_times [B][K][max_roots] (ascending; max_roots
+ * from minsnap_extrema_max_roots) and d_root_count [B][K]. */
+#define MINSNAP_EXTREMA_OPTIMIZATION 0
+#define MINSNAP_EXTREMA_TRAJECTORY 1
+#define MINSNAP_EXTREMA_KEEP_SMALL_COEFFICIENTS 16
+MINSNAP_API int minsnap_extrema_max_roots(int N, int derivative, int n_dims);
+MINSNAP_API int minsnap_extrema(long B, int K, int D, int N, const double* d_coeffs,
+                                const double* d_times, int derivative, int mode, uint32_t dim_mask,
+                                double* d_max_time, double* d_max_value, int32_t* d_max_segment,
+                                double* d_min_time, double* d_min_value, int32_t* d_min_segment,
+                                double* d_root_times, int32_t* d_root_count,
+                                minsnap_stream_t stream);
+
 /* ---- host-buffer entry points (synchronous; copies inside) -------------------------------
  * The calls a host program makes when its data lives in host memory.  Work is cut into
  * chunks that are copied and solved on alternating streams so that PCIe and the SMs overlap.
@@ -215,6 +249,13 @@ MINSNAP_API int minsnap_coeffs_from_constraints_host(long B, int K, int D, int N
                                                      const double* h_times, double* h_coeffs);
 MINSNAP_API int minsnap_cost_host(long B, int K, int D, int N, int derivative,
                                   const double* h_coeffs, const double* h_times, double* h_cost);
+
+MINSNAP_API int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs,
+                                     const double* h_times, int derivative, int mode,
+                                     uint32_t dim_mask, double* h_max_time, double* h_max_value,
+                                     int32_t* h_max_segment, double* h_min_time,
+                                     double* h_min_value, int32_t* h_min_segment,
+                                     double* h_root_times, int32_t* h_root_count);
 
 /* ---- a3: synthetic inputs (ref: createRandomVertices, src/vertex.cpp:27-79) -- HOST ONLY ----
  * positions[b] = vertex positions of createRandomVertices(., K, pos_min, pos_max, base_seed + b):

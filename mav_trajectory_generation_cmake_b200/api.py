@@ -234,9 +234,79 @@ def cost_sweep(positions, times, end_derivatives=None, N=10, derivative=SNAP, wa
     return (out, status) if want_status else out
 
 
+EXTREMA_OPTIMIZATION = 0   # PolynomialOptimization::computeMaximumOfMagnitude (ref LIN.i:470-503)
+EXTREMA_TRAJECTORY = 1     # Trajectory::computeMinMaxMagnitude (ref src/trajectory.cpp:181-217)
+EXTREMA_KEEP_SMALL_COEFFICIENTS = 16   # OR into mode: do not truncate coefficients below 2.2e-16
+
+
+def _dim_mask(D, dimensions):
+    if dimensions is None:
+        return (1 << D) - 1
+    m = 0
+    for d in dimensions:
+        if not 0 <= int(d) < D:
+            raise ValueError("dimension %r out of bounds [0..%d]" % (d, D - 1))
+        m |= 1 << int(d)
+    return m
+
+
+def extrema_max_roots(N, derivative, n_dims):
+    return _lib().minsnap_extrema_max_roots(N, derivative, n_dims)
+
+
+def extrema(coeffs, times, derivative, mode=EXTREMA_OPTIMIZATION, dimensions=None, want_roots=False):
+    """coeffs [B][K][D][N], times [B][K] (CUDA tensors) -> dict of [B] tensors: max_time, max_value,
+    max_segment (and min_* in EXTREMA_TRAJECTORY mode); with want_roots also root_times
+    [B][K][max_roots] and root_count [B][K].  Times are local to the reported segment."""
+    torch = _torch()
+    B, K, D, N = coeffs.shape
+    dev = coeffs.device
+    mask = _dim_mask(D, dimensions)
+    r = dict(max_time=torch.empty((B,), dtype=torch.float64, device=dev),
+             max_value=torch.empty((B,), dtype=torch.float64, device=dev),
+             max_segment=torch.empty((B,), dtype=torch.int32, device=dev))
+    if mode & ~EXTREMA_KEEP_SMALL_COEFFICIENTS == EXTREMA_TRAJECTORY:
+        r.update(min_time=torch.empty((B,), dtype=torch.float64, device=dev),
+                 min_value=torch.empty((B,), dtype=torch.float64, device=dev),
+                 min_segment=torch.empty((B,), dtype=torch.int32, device=dev))
+    if want_roots:
+        mr = extrema_max_roots(N, derivative, bin(mask).count("1"))
+        r["root_times"] = torch.zeros((B, K, max(mr, 1)), dtype=torch.float64, device=dev)
+        r["root_count"] = torch.empty((B, K), dtype=torch.int32, device=dev)
+    capi.check(_lib().minsnap_extrema(B, K, D, N, _dptr(coeffs, torch.float64), _dptr(times, torch.float64),
+                                      derivative, mode, mask, _dptr(r["max_time"]), _dptr(r["max_value"]),
+                                      _dptr(r["max_segment"]), _dptr(r.get("min_time")), _dptr(r.get("min_value")),
+                                      _dptr(r.get("min_segment")), _dptr(r.get("root_times")),
+                                      _dptr(r.get("root_count")), _stream()), "minsnap_extrema")
+    return r
+
+
 # ------------------------------------------------------------------------------------------
 # host-buffer entry points (numpy arrays, synchronous, copies inside)
 # ------------------------------------------------------------------------------------------
+def extrema_host(coeffs, times, derivative, mode=EXTREMA_OPTIMIZATION, dimensions=None, want_roots=False):
+    """numpy variant of extrema()."""
+    coeffs = _np(coeffs, np.float64)
+    times = _np(times, np.float64)
+    B, K, D, N = coeffs.shape
+    mask = _dim_mask(D, dimensions)
+    r = dict(max_time=np.empty((B,), np.float64), max_value=np.empty((B,), np.float64),
+             max_segment=np.empty((B,), np.int32))
+    if mode & ~EXTREMA_KEEP_SMALL_COEFFICIENTS == EXTREMA_TRAJECTORY:
+        r.update(min_time=np.empty((B,), np.float64), min_value=np.empty((B,), np.float64),
+                 min_segment=np.empty((B,), np.int32))
+    if want_roots:
+        mr = extrema_max_roots(N, derivative, bin(mask).count("1"))
+        r["root_times"] = np.zeros((B, K, max(mr, 1)), np.float64)
+        r["root_count"] = np.empty((B, K), np.int32)
+    capi.check(_lib().minsnap_extrema_host(B, K, D, N, _hptr(coeffs), _hptr(times), derivative, mode, mask,
+                                           _hptr(r["max_time"]), _hptr(r["max_value"]), _hptr(r["max_segment"]),
+                                           _hptr(r.get("min_time")), _hptr(r.get("min_value")),
+                                           _hptr(r.get("min_segment")), _hptr(r.get("root_times")),
+                                           _hptr(r.get("root_count"))), "minsnap_extrema_host")
+    return r
+
+
 def solve_host(mask, fixed_values, times, N=10, derivative=SNAP):
     mask = np.ascontiguousarray(mask, np.uint8)
     K = mask.shape[0] - 1

@@ -395,6 +395,43 @@ int minsnap_cost_sweep(long B, int S, int K, int D, int N, int derivative, const
   return MINSNAP_OK;
 }
 
+// extrema of |p^(k)| (ref LIN.i:470-503, src/trajectory.cpp:181-217)
+static bool extrema_args_ok(long B, int K, int D, int N, int derivative, int mode, uint32_t* dim_mask) {
+  const int base = mode & ~MINSNAP_EXTREMA_KEEP_SMALL_COEFFICIENTS;
+  if (B < 0 || K < 1 || D < 1 || D > 32 || !minsnap::supported_n(N) || derivative < 0 || derivative > N - 2 ||
+      (base != MINSNAP_EXTREMA_OPTIMIZATION && base != MINSNAP_EXTREMA_TRAJECTORY))
+    return false;
+  const uint32_t all = D == 32 ? 0xffffffffu : ((1u << D) - 1u);
+  if (*dim_mask == 0) *dim_mask = all;
+  return (*dim_mask & ~all) == 0;
+}
+
+int minsnap_extrema_max_roots(int N, int derivative, int n_dims) {
+  if (!minsnap::supported_n(N) || derivative < 0 || derivative > N - 2 || n_dims < 1) return 0;
+  return minsnap::extrema_max_roots(N, derivative, n_dims);
+}
+
+int minsnap_extrema(long B, int K, int D, int N, const double* d_coeffs, const double* d_times, int derivative,
+                    int mode, uint32_t dim_mask, double* d_max_time, double* d_max_value, int32_t* d_max_segment,
+                    double* d_min_time, double* d_min_value, int32_t* d_min_segment, double* d_root_times,
+                    int32_t* d_root_count, minsnap_stream_t stream) {
+  if (!extrema_args_ok(B, K, D, N, derivative, mode, &dim_mask)) return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  if (!d_coeffs || !d_times) return MINSNAP_ERR_ARG;
+  minsnap::ExtremaArgs a;
+  a.B = B; a.K = K; a.D = D; a.N = N; a.derivative = derivative;
+  a.mode = mode & ~MINSNAP_EXTREMA_KEEP_SMALL_COEFFICIENTS;
+  a.keep_small = (mode & MINSNAP_EXTREMA_KEEP_SMALL_COEFFICIENTS) != 0;
+  a.dim_mask = dim_mask;
+  a.d_coeffs = d_coeffs; a.d_times = d_times;
+  a.d_max_time = d_max_time; a.d_max_value = d_max_value; a.d_max_segment = d_max_segment;
+  a.d_min_time = d_min_time; a.d_min_value = d_min_value; a.d_min_segment = d_min_segment;
+  a.d_root_times = d_root_times; a.d_root_count = d_root_count;
+  a.max_roots = minsnap::extrema_max_roots(N, derivative, __builtin_popcount(dim_mask));
+  CU(minsnap::launch_extrema(a, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // Host-buffer entry points
 // ---------------------------------------------------------------------------------------
@@ -604,6 +641,78 @@ int minsnap_cost_host(long B, int K, int D, int N, int derivative, const double*
     rc = minsnap_cost(B, K, D, N, derivative, co.as<double>(), tm.as<double>(), cs.as<double>(), st);
     if (rc != MINSNAP_OK) goto done;
     TRY(cudaMemcpyAsync(h_cost, cs.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+  done:;
+  }
+  cudaError_t es = cudaStreamSynchronize(st);
+  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  return rc;
+}
+
+int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs, const double* h_times, int derivative,
+                         int mode, uint32_t dim_mask, double* h_max_time, double* h_max_value,
+                         int32_t* h_max_segment, double* h_min_time, double* h_min_value, int32_t* h_min_segment,
+                         double* h_root_times, int32_t* h_root_count) {
+  if (!extrema_args_ok(B, K, D, N, derivative, mode, &dim_mask)) return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  if (!h_coeffs || !h_times) return MINSNAP_ERR_ARG;
+  const size_t nb = (size_t)B;
+  const size_t max_roots = (size_t)minsnap::extrema_max_roots(N, derivative, __builtin_popcount(dim_mask));
+  const size_t root_bytes = sizeof(double) * nb * K * (max_roots ? max_roots : 1);
+  {
+    SmallCall sc(cudaStreamPerThread);
+    const int i_coeffs = sc.in(h_coeffs, sizeof(double) * nb * K * D * N);
+    const int i_times = sc.in(h_times, sizeof(double) * nb * K);
+    const int o_xt = sc.out(h_max_time, sizeof(double) * nb);
+    const int o_xv = sc.out(h_max_value, sizeof(double) * nb);
+    const int o_xs = sc.out(h_max_segment, sizeof(int32_t) * nb);
+    const int o_nt = sc.out(h_min_time, sizeof(double) * nb);
+    const int o_nv = sc.out(h_min_value, sizeof(double) * nb);
+    const int o_ns = sc.out(h_min_segment, sizeof(int32_t) * nb);
+    const int o_rt = h_root_times ? sc.out(h_root_times, root_bytes) : -1;
+    const int o_rc = h_root_count ? sc.out(h_root_count, sizeof(int32_t) * nb * K) : -1;
+    if (sc.total_bytes() <= kSmallCallBytes) {
+      CU(sc.upload());
+      const int rc = minsnap_extrema(B, K, D, N, sc.dev<double>(i_coeffs), sc.dev<double>(i_times), derivative, mode,
+                                     dim_mask, sc.dev<double>(o_xt), sc.dev<double>(o_xv), sc.dev<int32_t>(o_xs),
+                                     sc.dev<double>(o_nt), sc.dev<double>(o_nv), sc.dev<int32_t>(o_ns),
+                                     o_rt >= 0 ? sc.dev<double>(o_rt) : nullptr,
+                                     o_rc >= 0 ? sc.dev<int32_t>(o_rc) : nullptr, cudaStreamPerThread);
+      if (rc != MINSNAP_OK) return rc;
+      CU(sc.download());
+      return MINSNAP_OK;
+    }
+  }
+  cudaStream_t st = cudaStreamPerThread;
+  int rc = MINSNAP_OK;
+  {
+    Scratch co, tm, xt, xv, xs, nt, nv, ns, rt, rcnt;
+    TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
+    TRY(tm.alloc(sizeof(double) * nb * K, st));
+    TRY(xt.alloc(sizeof(double) * nb, st));
+    TRY(xv.alloc(sizeof(double) * nb, st));
+    TRY(xs.alloc(sizeof(int32_t) * nb, st));
+    TRY(nt.alloc(sizeof(double) * nb, st));
+    TRY(nv.alloc(sizeof(double) * nb, st));
+    TRY(ns.alloc(sizeof(int32_t) * nb, st));
+    if (h_root_times) TRY(rt.alloc(root_bytes, st));
+    if (h_root_count) TRY(rcnt.alloc(sizeof(int32_t) * nb * K, st));
+    TRY(cudaMemcpyAsync(co.ptr, h_coeffs, sizeof(double) * nb * K * D * N, cudaMemcpyHostToDevice, st));
+    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
+    rc = minsnap_extrema(B, K, D, N, co.as<double>(), tm.as<double>(), derivative, mode, dim_mask, xt.as<double>(),
+                         xv.as<double>(), xs.as<int32_t>(), nt.as<double>(), nv.as<double>(), ns.as<int32_t>(),
+                         h_root_times ? rt.as<double>() : nullptr, h_root_count ? rcnt.as<int32_t>() : nullptr, st);
+    if (rc != MINSNAP_OK) goto done;
+    if (h_max_time) TRY(cudaMemcpyAsync(h_max_time, xt.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+    if (h_max_value) TRY(cudaMemcpyAsync(h_max_value, xv.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+    if (h_max_segment) TRY(cudaMemcpyAsync(h_max_segment, xs.ptr, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+    if ((mode & ~MINSNAP_EXTREMA_KEEP_SMALL_COEFFICIENTS) == MINSNAP_EXTREMA_TRAJECTORY) {
+      if (h_min_time) TRY(cudaMemcpyAsync(h_min_time, nt.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+      if (h_min_value) TRY(cudaMemcpyAsync(h_min_value, nv.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+      if (h_min_segment) TRY(cudaMemcpyAsync(h_min_segment, ns.ptr, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_root_times) TRY(cudaMemcpyAsync(h_root_times, rt.ptr, root_bytes, cudaMemcpyDeviceToHost, st));
+    if (h_root_count)
+      TRY(cudaMemcpyAsync(h_root_count, rcnt.ptr, sizeof(int32_t) * nb * K, cudaMemcpyDeviceToHost, st));
   done:;
   }
   cudaError_t es = cudaStreamSynchronize(st);

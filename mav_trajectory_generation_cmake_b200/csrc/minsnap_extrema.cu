@@ -1,0 +1,308 @@
+// Extrema of the magnitude of a derivative over solved trajectories.
+//
+// Reference (relative to /root/reference/mav_trajectory_generation/, LIN.i =
+// include/mav_trajectory_generation/impl/polynomial_optimization_linear_impl.h):
+//   PolynomialOptimization::computeMaximumOfMagnitude            LIN.i:470-503   (mode 0)
+//   PolynomialOptimization::computeSegmentMaximumMagnitudeCandidates  LIN.i:378-437
+//   Trajectory::computeMinMaxMagnitude                            src/trajectory.cpp:181-217 (mode 1)
+//   Segment::computeMinMaxMagnitudeCandidate[Time]s, selectMinMaxMagnitudeFromCandidates
+//                                                                 src/segment.cpp:82-199
+//   Polynomial::convolve src/polynomial.cpp:157-175, getCoefficients polynomial.h:100-117,
+//   trailing-coefficient removal src/rpoly.cpp:44-75.
+//
+// Candidate times of a segment are the real roots inside [0, T] of
+//   g(t) = sum_dim p_dim^(k)(t) p_dim^(k+1)(t)        (several dimensions; d/dt of |p^(k)|^2 / 2)
+//   g(t) = p^(k+1)(t)                                   (one dimension)
+// The reference hands g to a Jenkins-Traub root finder (TOMS 493, serial, global state) and keeps
+// the real roots in range.  Here every thread owns one segment and isolates the real roots
+// directly: the real roots of g^(m+1) split [0, T] into intervals on which g^(m) is monotone, so
+// each sign change brackets exactly one root, refined by a safeguarded Newton iteration; the
+// recursion starts at the linear derivative.  No complex arithmetic, no deflation, fixed-size
+// state (4 arrays of <= 24 doubles), and every thread of a warp runs the same level at the same
+// time.  A second kernel folds the per-segment results in the reference's candidate order.
+#include <cfloat>
+
+#include "minsnap_device.cuh"
+#include "minsnap_launch.h"
+
+namespace minsnap {
+
+namespace {
+
+constexpr int kMaxG = 24;  // coefficients of g: 2N - 2k - 2 <= 22 for N <= 12
+
+struct SegmentExtremum {
+  double max_t, max_v, min_t, min_v;
+};
+
+// C(i, m) for i < 24: derivative level m of g divided by m! has coefficients C(j+m, m) g[j+m].
+__constant__ double c_binomial[kMaxG][kMaxG];
+
+struct PolyView {
+  const double* d;
+  int deg;
+  __device__ __forceinline__ void eval(double t, double& f, double& fp) const {
+    double a = d[deg], b = 0.0;
+    for (int j = deg - 1; j >= 0; --j) {
+      b = fma(b, t, a);
+      a = fma(a, t, d[j]);
+    }
+    f = a;
+    fp = b;
+  }
+  __device__ __forceinline__ double value(double t) const {
+    double a = d[deg];
+    for (int j = deg - 1; j >= 0; --j) a = fma(a, t, d[j]);
+    return a;
+  }
+};
+
+// One root of a monotone piece: f(lo) and f(hi) have opposite signs.
+__device__ double refine_bracket(const PolyView& p, double lo, double hi, bool lo_negative) {
+  double x = 0.5 * (lo + hi);
+  for (int it = 0; it < 128; ++it) {
+    double f, fp;
+    p.eval(x, f, fp);
+    if (f == 0.0) return x;
+    if ((f < 0.0) == lo_negative) lo = x; else hi = x;
+    double next = fp != 0.0 ? x - f / fp : lo - 1.0;
+    if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);
+    if (next == lo || next == hi) return next;
+    if (fabs(next - x) <= 2.0 * DBL_EPSILON * fabs(next)) return next;
+    x = next;
+  }
+  return x;
+}
+
+// Real roots of g (n coefficients, increasing, g[n-1] != 0) inside [t0, t1], ascending.
+// prev/cur/d: scratch of kMaxG doubles each.  Returns the count; the roots are in `prev`.
+__device__ int real_roots_in_range(const double* g, int n, double t0, double t1, double* prev, double* cur,
+                                   double* d) {
+  const int deg = n - 1;
+  int n_prev = 0;
+  for (int m = deg - 1; m >= 0; --m) {
+    const int dm = deg - m;
+    for (int j = 0; j <= dm; ++j) d[j] = c_binomial[j + m][m] * g[j + m];
+    const PolyView p{d, dm};
+    int n_cur = 0;
+    double left = t0;
+    double f_left = p.value(left);
+    if (f_left == 0.0) cur[n_cur++] = left;
+    for (int i = 0; i <= n_prev; ++i) {
+      const double right = i < n_prev ? prev[i] : t1;
+      if (!(right > left)) continue;
+      const double f_right = p.value(right);
+      if (f_right == 0.0) {
+        cur[n_cur++] = right;
+      } else if (f_left != 0.0 && (f_left < 0.0) != (f_right < 0.0)) {
+        cur[n_cur++] = refine_bracket(p, left, right, f_left < 0.0);
+      }
+      left = right;
+      f_left = f_right;
+    }
+    for (int i = 0; i < n_cur; ++i) prev[i] = cur[i];
+    n_prev = n_cur;
+  }
+  return n_prev;
+}
+
+struct ExtremaParams {
+  long B;
+  int K, D, N, derivative, mode;
+  bool keep_small;
+  uint32_t dim_mask;
+  const double* coeffs;
+  const double* times;
+  SegmentExtremum* per_segment;  // [B][K]
+  double* root_times;            // optional [B][K][max_roots]
+  int32_t* root_count;           // optional [B][K]
+  int max_roots;
+};
+
+// ref polynomial.h:138-151 (Horner with the base coefficient folded in at every step)
+__device__ inline double evaluate_derivative(const double* c, int N, int k, double t) {
+  if (k >= N) return 0.0;
+  double r = falling_factorial(k, N - 1) * c[N - 1];
+  for (int j = N - 2; j >= k; --j) {
+    r *= t;
+    r += falling_factorial(k, j) * c[j];
+  }
+  return r;
+}
+
+__device__ inline double magnitude_at(const double* seg, int D, int N, uint32_t mask, int k, double t) {
+  double s = 0.0;
+  for (int dim = 0; dim < D; ++dim) {
+    if (!((mask >> dim) & 1u)) continue;
+    const double v = evaluate_derivative(seg + dim * N, N, k, t);
+    s += v * v;
+  }
+  return sqrt(s);
+}
+
+__global__ void __launch_bounds__(128) segment_extrema_kernel(ExtremaParams p) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.B * p.K) return;
+  const int N = p.N, D = p.D, k = p.derivative;
+  const double* seg = p.coeffs + idx * D * N;
+  const double T = p.times[idx];
+  const int n_dims = __popc(p.dim_mask);
+
+  double g[kMaxG], d[kMaxG], ra[kMaxG], rb[kMaxG];
+  int len;
+  const int n_d = N - k, n_dd = n_d - 1;
+  if (n_dims > 1) {
+    // g = sum over dimensions of convolve(d, dd) (ref LIN.i:396-404 / src/segment.cpp:103-112);
+    // convolve sums kernel[j] data[i-j] from the highest j down (src/polynomial.cpp:164-172).
+    len = n_d + n_dd - 1;
+    for (int i = 0; i < len; ++i) g[i] = 0.0;
+    for (int dim = 0; dim < D; ++dim) {
+      if (!((p.dim_mask >> dim) & 1u)) continue;
+      const double* c = seg + dim * N;
+      for (int j = 0; j < n_d; ++j) ra[j] = c[j + k] * falling_factorial(k, j + k);             // d
+      for (int j = 0; j < n_dd; ++j) rb[j] = c[j + k + 1] * falling_factorial(k + 1, j + k + 1); // dd
+      for (int i = 0; i < len; ++i) {
+        const int j_hi = min(n_dd - 1, i), j_lo = max(0, i - (n_d - 1));
+        double acc = 0.0;
+        for (int j = j_hi; j >= j_lo; --j) acc += rb[j] * ra[i - j];
+        g[i] += acc;
+      }
+    }
+  } else {
+    // one dimension: the roots of the next derivative (ref LIN.i:412-416, src/polynomial.cpp:57-78)
+    int dim = 0;
+    while (dim < D - 1 && !((p.dim_mask >> dim) & 1u)) ++dim;
+    const double* c = seg + dim * N;
+    len = n_dd;
+    for (int j = 0; j < n_dd; ++j) g[j] = c[j + k + 1] * falling_factorial(k + 1, j + k + 1);
+  }
+  // ref src/rpoly.cpp:44-55: drop trailing coefficients below machine epsilon.  The threshold is
+  // absolute, so on long segments (T above ~12 s) the reference truncates coefficients that
+  // matter near t = T; reproduced by default, keep_small removes exact zeros only.
+  int last = len - 1;
+  if (p.keep_small) {
+    while (last >= 0 && g[last] == 0.0) --last;
+  } else {
+    while (last >= 0 && !(fabs(g[last]) >= DBL_EPSILON)) --last;
+  }
+  int n_roots = 0;
+  if (last >= 1 && T >= 0.0) n_roots = real_roots_in_range(g, last + 1, 0.0, T, ra, rb, d);
+  const double* roots = ra;
+
+  if (p.root_count) p.root_count[idx] = n_roots;
+  if (p.root_times)
+    for (int i = 0; i < n_roots && i < p.max_roots; ++i) p.root_times[idx * p.max_roots + i] = roots[i];
+
+  SegmentExtremum e;
+  const bool last_segment = (idx % p.K) == p.K - 1;
+  if (p.mode == 0) {
+    // candidates: 0, roots, (last segment only) T; strictly larger replaces (LIN.i:486-499)
+    e.max_t = 0.0;
+    e.max_v = magnitude_at(seg, D, N, p.dim_mask, k, 0.0);
+    for (int i = 0; i < n_roots; ++i) {
+      const double v = magnitude_at(seg, D, N, p.dim_mask, k, roots[i]);
+      if (e.max_v < v) { e.max_v = v; e.max_t = roots[i]; }
+    }
+    if (last_segment) {
+      const double v = magnitude_at(seg, D, N, p.dim_mask, k, T);
+      if (e.max_v < v) { e.max_v = v; e.max_t = T; }
+    }
+    e.min_t = 0.0;
+    e.min_v = 0.0;
+  } else {
+    // candidates: start, end, roots (src/polynomial.cpp:39-40, src/segment.cpp:171-179)
+    e.max_t = e.min_t = 0.0;
+    e.max_v = e.min_v = magnitude_at(seg, D, N, p.dim_mask, k, 0.0);
+    for (int i = -1; i < n_roots; ++i) {
+      const double t = i < 0 ? T : roots[i];
+      const double v = magnitude_at(seg, D, N, p.dim_mask, k, t);
+      if (e.max_v < v) { e.max_v = v; e.max_t = t; }
+      if (v < e.min_v) { e.min_v = v; e.min_t = t; }
+    }
+  }
+  p.per_segment[idx] = e;
+}
+
+struct FoldParams {
+  long B;
+  int K, mode;
+  const SegmentExtremum* per_segment;
+  double *max_time, *max_value, *min_time, *min_value;
+  int32_t *max_segment, *min_segment;
+};
+
+__global__ void __launch_bounds__(128) fold_extrema_kernel(FoldParams p) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const SegmentExtremum* e = p.per_segment + b * p.K;
+  // mode 0 starts from Extremum() = (0, 0, 0) (LIN.i:477); mode 1 from lowest()/max() (src/trajectory.cpp:186-187)
+  double max_t = 0.0, max_v = p.mode == 0 ? 0.0 : -DBL_MAX, min_t = 0.0, min_v = DBL_MAX;
+  int max_s = 0, min_s = 0;
+  for (int s = 0; s < p.K; ++s) {
+    const SegmentExtremum c = e[s];
+    if (c.max_v > max_v) { max_v = c.max_v; max_t = c.max_t; max_s = s; }
+    if (p.mode != 0 && c.min_v < min_v) { min_v = c.min_v; min_t = c.min_t; min_s = s; }
+  }
+  if (p.max_time) p.max_time[b] = max_t;
+  if (p.max_value) p.max_value[b] = max_v;
+  if (p.max_segment) p.max_segment[b] = max_s;
+  if (p.mode != 0) {
+    if (p.min_time) p.min_time[b] = min_t;
+    if (p.min_value) p.min_value[b] = min_v;
+    if (p.min_segment) p.min_segment[b] = min_s;
+  }
+}
+
+cudaError_t upload_binomials() {
+  static cudaError_t status = [] {
+    static double h[kMaxG][kMaxG];
+    for (int i = 0; i < kMaxG; ++i)
+      for (int m = 0; m < kMaxG; ++m) {
+        if (m > i) { h[i][m] = 0.0; continue; }
+        // exact in double: C(23, 11) = 1,352,078
+        double c = 1.0;
+        for (int q = 1; q <= m; ++q) c = c * (double)(i - m + q) / (double)q;
+        h[i][m] = c;
+      }
+    return cudaMemcpyToSymbol(c_binomial, h, sizeof(h));
+  }();
+  return status;
+}
+
+}  // namespace
+
+int extrema_max_roots(int N, int derivative, int n_dims) {
+  const int n_d = N - derivative, n_dd = n_d - 1;
+  const int len = n_dims > 1 ? n_d + n_dd - 1 : n_dd;
+  return len > 1 ? len - 1 : 0;
+}
+
+cudaError_t launch_extrema(const ExtremaArgs& a, cudaStream_t stream) {
+  if (a.B == 0) return cudaSuccess;
+  cudaError_t e = upload_binomials();
+  if (e != cudaSuccess) return e;
+  void* scratch = nullptr;
+  if ((e = cudaMallocAsync(&scratch, sizeof(SegmentExtremum) * (size_t)a.B * a.K, stream)) != cudaSuccess) return e;
+  ExtremaParams p;
+  p.B = a.B; p.K = a.K; p.D = a.D; p.N = a.N; p.derivative = a.derivative; p.mode = a.mode;
+  p.keep_small = a.keep_small;
+  p.dim_mask = a.dim_mask;
+  p.coeffs = a.d_coeffs; p.times = a.d_times;
+  p.per_segment = static_cast<SegmentExtremum*>(scratch);
+  p.root_times = a.d_root_times; p.root_count = a.d_root_count; p.max_roots = a.max_roots;
+  const long n = a.B * a.K;
+  segment_extrema_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    FoldParams f;
+    f.B = a.B; f.K = a.K; f.mode = a.mode; f.per_segment = p.per_segment;
+    f.max_time = a.d_max_time; f.max_value = a.d_max_value; f.max_segment = a.d_max_segment;
+    f.min_time = a.d_min_time; f.min_value = a.d_min_value; f.min_segment = a.d_min_segment;
+    fold_extrema_kernel<<<(unsigned)((a.B + 127) / 128), 128, 0, stream>>>(f);
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(scratch, stream);
+  return e;
+}
+
+}  // namespace minsnap

@@ -85,6 +85,28 @@ cudaError_t launch_evaluate_range(long B, int K, int D, int N, const double* d_c
                                   int derivative, int max_samples, double* d_out, double* d_t_out,
                                   int32_t* d_count, cudaStream_t stream);
 
+// ---- minsnap_extrema.cu ----------------------------------------------------------------
+struct ExtremaArgs {
+  long B;
+  int K, D, N, derivative;
+  int mode;            // 0: computeMaximumOfMagnitude (LIN.i:470-503), 1: Trajectory::computeMinMaxMagnitude
+  bool keep_small;     // false: drop trailing coefficients below machine epsilon like the reference
+  uint32_t dim_mask;   // dimensions that take part (never 0 here)
+  const double* d_coeffs;
+  const double* d_times;
+  double* d_max_time;      // [B] each, optional
+  double* d_max_value;
+  int32_t* d_max_segment;
+  double* d_min_time;      // mode 1 only
+  double* d_min_value;
+  int32_t* d_min_segment;
+  double* d_root_times;    // optional [B][K][max_roots]
+  int32_t* d_root_count;   // optional [B][K]
+  int max_roots;
+};
+int extrema_max_roots(int N, int derivative, int n_dims);
+cudaError_t launch_extrema(const ExtremaArgs& a, cudaStream_t stream);
+
 // ---- minsnap_peak.cu -------------------------------------------------------------------
 cudaError_t run_fp64_peak(int repeats, double* tflops);
 

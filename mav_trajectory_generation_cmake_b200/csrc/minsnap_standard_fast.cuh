@@ -221,10 +221,12 @@ __host__ __device__ inline int lane_slots(int K) {
 }
 
 template <int D>
-__host__ __device__ inline size_t warp_smem_doubles(int K, bool global_slots = false) {
+__host__ __device__ inline size_t warp_smem_doubles(int K, bool global_slots = false, bool direct = false) {
   // [slots][32] + positions [16][(K+1) D] + times [16][K]; every region a multiple of 16 bytes.
   // Long chains keep the slots in global memory (coalesced: one 256-byte row per slot).
+  // Direct mode reads positions / times straight from global memory (no staging area).
   const size_t slots = global_slots ? 0 : ((size_t)lane_slots<D>(K) * kSlotStride + 1) & ~(size_t)1;
+  if (direct) return slots;
   const size_t pos = ((size_t)kPairsPerWarp * (K + 1) * D + 1) & ~(size_t)1;
   const size_t tim = ((size_t)kPairsPerWarp * K + 1) & ~(size_t)1;
   return slots + pos + tim;
@@ -245,7 +247,12 @@ __device__ __forceinline__ void async_copy_doubles(double* dst, const double* sr
 // ------------------------------------------------------------------------------------------
 // The kernel.  kCoeffs: recover and store coefficients; cost is computed when p.cost != NULL.
 // ------------------------------------------------------------------------------------------
-template <int D, bool kCoeffs, bool kGlobalSlots = false, bool kCost = true>
+// kDirect: positions / times are read straight from global memory instead of being staged in
+// shared memory.  Measured on B200: the cost sweep (64 time allocations share one set of
+// positions, so the loads broadcast) gains 22 % (394 -> 308 us); the coefficient kernel loses 4 %
+// and stays staged.  Capping registers at 168 for 10-12 resident warps was measured too: the
+// spills and lost ILP cost 27 % per warp, more than the extra warps return.
+template <int D, bool kCoeffs, bool kGlobalSlots = false, bool kCost = true, bool kDirect = false>
 __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
@@ -254,7 +261,7 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
   const int K = p.K;
   const int pos_stride = (K + 1) * D;
   const int time_stride = K;
-  double* wbase = smem + (size_t)warp * warp_smem_doubles<D>(K, kGlobalSlots);
+  double* wbase = smem + (size_t)warp * warp_smem_doubles<D>(K, kGlobalSlots, kDirect);
   double* slots = kGlobalSlots ? p.slot_scratch + ((size_t)blockIdx.x * warps_per_cta + warp) *
                                                       ((size_t)lane_slots<D>(K) * kSlotStride)
                                : wbase;                                  // [n_slots][32]
@@ -299,13 +306,14 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
   // boundary / middle vectors during coefficient recovery)
   const int landing_slot = kF * D * n_stored + 3 * kF * D;
   double* landing = slots + (size_t)landing_slot * kSlotStride;
-  const bool can_prefetch = !kGlobalSlots &&
+  const bool can_prefetch = !kGlobalSlots && !kDirect &&
                             (kBlockSlots * n_stored - 3 * kF * D) * kSlotStride >= pos_doubles + time_doubles &&
                             ((landing_slot * kSlotStride) & 1) == 0;
   const long stride = (long)gridDim.x * pairs_per_cta;
   const long first = (long)blockIdx.x * pairs_per_cta + (long)warp * kPairsPerWarp;
   bool landed = false;
-  if (first < n_problems) issue_inputs(pos_s, time_s, first, (int)min((long)kPairsPerWarp, n_problems - first));
+  if (!kDirect && first < n_problems)
+    issue_inputs(pos_s, time_s, first, (int)min((long)kPairsPerWarp, n_problems - first));
 
   for (long base = first; base < n_problems; base += stride) {
     const int n_here = (int)min((long)kPairsPerWarp, n_problems - base);
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
     const long prob = base + q;          // problem of this pair
     const bool active = q < n_here;
     // ---- inputs of this batch ---------------------------------------------------------------
-    {
+    if (!kDirect) {
       __pipeline_wait_prior(0);
       __syncwarp();
       if (landed) {
@@ -343,8 +351,11 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
       }
     }
 
-    const double* my_pos = pos_s + q * pos_stride;
-    const double* my_time = time_s + q * time_stride;
+    // direct mode: idle lanes of a ragged last batch recompute the last problem (stores are masked)
+    const long prob_in = active ? prob : n_problems - 1;
+    const double* my_pos = kDirect ? p.positions + (p.sweep_S > 0 ? prob_in / p.sweep_S : prob_in) * per_pos
+                                   : pos_s + q * pos_stride;
+    const double* my_time = kDirect ? p.times + prob_in * K : time_s + q * time_stride;
     // local chain: vertex j <-> actual vertex (side ? K - j : j); segment j (between local
     // vertices j and j+1) <-> actual segment (side ? K-1-j : j)
     auto local_T = [&](int j) { return my_time[side ? K - 1 - j : j]; };
@@ -818,7 +829,7 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
     if (nonfinite) status |= 4;
     status |= __shfl_xor_sync(0xffffffffu, status, 1);
     if (p.status && active && side == 0) p.status[prob] = status;
-    if (n_next > 0 && !can_prefetch) {
+    if (!kDirect && n_next > 0 && !can_prefetch) {
       __syncwarp();   // every lane is done with this batch's inputs
       issue_inputs(pos_s, time_s, next_base, n_next);
       landed = false;
@@ -841,9 +852,9 @@ inline bool supported(int K, int D, int N, int derivative) {
 }
 inline bool sweep_supported(int K, int D, int N, int derivative) { return supported(K, D, N, derivative); }
 
-template <int D, bool kCoeffs, bool kGlobalSlots>
+template <int D, bool kCoeffs, bool kGlobalSlots, bool kDirect = false>
 inline cudaError_t launch_mode(FastParams p, cudaStream_t stream) {
-  const size_t per_warp = warp_smem_doubles<D>(p.K, kGlobalSlots) * sizeof(double);
+  const size_t per_warp = warp_smem_doubles<D>(p.K, kGlobalSlots, kDirect) * sizeof(double);
   // warps per CTA that maximise resident warps per SM (shared memory is the limiter; each CTA
   // also costs 1 KB of reserved shared memory)
   int warps = 1, best = 0;
@@ -870,8 +881,8 @@ inline cudaError_t launch_mode(FastParams p, cudaStream_t stream) {
     if (need > smem && need <= kMaxDynamicSmem && (228 * 1024) / (need + 1024) == (size_t)cap) smem = need;
   }
   // the cost path is compiled out when no cost is requested (smaller hot loop, fewer registers)
-  void (*kernel)(FastParams) = p.cost ? solve_standard_pair_kernel<D, kCoeffs, kGlobalSlots, true>
-                                      : solve_standard_pair_kernel<D, kCoeffs, kGlobalSlots, false>;
+  void (*kernel)(FastParams) = p.cost ? solve_standard_pair_kernel<D, kCoeffs, kGlobalSlots, true, kDirect>
+                                      : solve_standard_pair_kernel<D, kCoeffs, kGlobalSlots, false, kDirect>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long n_problems = p.sweep_S > 0 ? p.B * p.sweep_S : p.B;
@@ -903,7 +914,13 @@ inline cudaError_t launch_mode(FastParams p, cudaStream_t stream) {
 
 template <int D, bool kCoeffs>
 inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
-  if (p.K <= kMaxK) return launch_mode<D, kCoeffs, false>(p, stream);
+  if (p.K <= kMaxK) {
+    // MINSNAP_TUNE_DIRECT=0/1 overrides the measured default (direct for the cost sweep only)
+    static const int tune = [] { const char* v = std::getenv("MINSNAP_TUNE_DIRECT"); return v ? std::atoi(v) : -1; }();
+    const bool direct = tune >= 0 ? tune == 1 : (!kCoeffs && p.sweep_S > 0);
+    if (direct && p.times) return launch_mode<D, kCoeffs, false, true>(p, stream);
+    return launch_mode<D, kCoeffs, false>(p, stream);
+  }
   return launch_mode<D, kCoeffs, true>(p, stream);
 }
 

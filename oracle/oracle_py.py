@@ -20,7 +20,7 @@ def build(force=False):
     """Compile both oracle shared objects with oracle/Makefile (gcc, seconds)."""
     need = force or not all(
         os.path.exists(os.path.join(_LIBDIR, n)) for n in ("liboracle_f64.so", "liboracle_ld.so"))
-    src_m = os.path.getmtime(os.path.join(_HERE, "minsnap_oracle.c"))
+    src_m = max(os.path.getmtime(os.path.join(_HERE, n)) for n in ("minsnap_oracle.c", "extrema_oracle.c"))
     if not need:
         need = any(os.path.getmtime(os.path.join(_LIBDIR, n)) < src_m
                    for n in ("liboracle_f64.so", "liboracle_ld.so"))
@@ -38,6 +38,7 @@ class Oracle:
         assert self.lib.orc_real_bytes() == np.dtype(self.real).itemsize
         self.lib.orc_polynomial_evaluate.restype = self.creal
         self.lib.orc_compute_cost.restype = self.creal
+        self.lib.orc_segment_magnitude.restype = self.creal
         self.precision = precision
 
     # -- helpers -------------------------------------------------------------------
@@ -210,6 +211,71 @@ class Oracle:
         return coeffs, cost, st
 
 
+    # -- extrema of the magnitude of a derivative (oracle/extrema_oracle.c) ------------------
+    @staticmethod
+    def _dims(D, dims):
+        d = np.ascontiguousarray(np.arange(D) if dims is None else np.asarray(dims), dtype=np.int32)
+        return d
+
+    def candidate_polynomial(self, seg_coeffs, derivative, dims=None):
+        """seg_coeffs [D][N] -> coefficients (increasing) of the polynomial whose real roots are
+        the candidate times, before trailing-coefficient removal."""
+        c = self._r(seg_coeffs)
+        D, N = c.shape
+        d = self._dims(D, dims)
+        g = np.zeros(2 * N, self.real)
+        n = self.lib.orc_candidate_polynomial(N, D, self._p(c), C.c_int(derivative), self._p(d), len(d), self._p(g))
+        return g[:n].copy()
+
+    def last_nonzero_coefficient(self, g):
+        g = self._r(g)
+        return self.lib.orc_last_nonzero_coefficient(self._p(g), len(g))
+
+    def real_roots_in_range(self, g, t0, t1):
+        g = self._r(g)
+        out = np.zeros(max(len(g), 1), self.real)
+        n = self.lib.orc_real_roots_in_range(self._p(g), len(g), self.creal(t0), self.creal(t1), self._p(out))
+        return out[:n].copy()
+
+    def segment_candidate_roots(self, seg_coeffs, derivative, t_start, t_end, dims=None, keep_small=False):
+        c = self._r(seg_coeffs)
+        D, N = c.shape
+        d = self._dims(D, dims)
+        out = np.zeros(2 * N, self.real)
+        n = self.lib.orc_segment_candidate_roots(N, D, self._p(c), C.c_int(derivative), self._p(d), len(d),
+                                                 self.creal(t_start), self.creal(t_end), C.c_int(int(keep_small)),
+                                                 self._p(out))
+        return out[:n].copy()
+
+    def minmax_magnitude(self, coeffs, times, derivative, mode, dims=None, want_candidates=False,
+                         keep_small=False):
+        """coeffs [K][D][N], times [K].  mode 0: computeMaximumOfMagnitude; mode 1:
+        Trajectory::computeMinMaxMagnitude.  Returns dict(max=(t, v, seg), min=(t, v, seg)[,
+        candidates=list of per-segment root arrays])."""
+        c = self._r(coeffs)
+        K, D, N = c.shape
+        tm = self._r(times).reshape(K)
+        d = self._dims(D, dims)
+        out = np.zeros(6, self.real)
+        max_cand = 2 * N
+        ct = np.zeros((K, max_cand), self.real)
+        cc = np.zeros(K, np.int32)
+        self.lib.orc_minmax_magnitude(C.c_int(mode), K, D, N, self._p(c), self._p(tm), C.c_int(derivative),
+                                      self._p(d), len(d), C.c_int(int(keep_small)), self._p(out), self._p(ct),
+                                      self._p(cc), max_cand)
+        r = {"max": (out[0], out[1], int(out[2])), "min": (out[3], out[4], int(out[5]))}
+        if want_candidates:
+            r["candidates"] = [ct[s, :cc[s]].copy() for s in range(K)]
+        return r
+
+    def segment_magnitude(self, seg_coeffs, derivative, t, dims=None):
+        c = self._r(seg_coeffs)
+        D, N = c.shape
+        d = self._dims(D, dims)
+        return self.lib.orc_segment_magnitude(N, D, self._p(c), C.c_int(derivative), self._p(d), len(d),
+                                              self.creal(t))
+
+
 def standard_mask(K, N=10, max_fixed_derivative=4):
     """Mask produced by createRandomVertices (src/vertex.cpp:59,71-76): end vertices fix
     derivatives 0..max_fixed_derivative, interior vertices fix position only."""
@@ -228,3 +294,39 @@ def vertex_values_from_positions(positions, N=10):
     v = np.zeros((K1, N // 2, D), positions.dtype)
     v[:, 0, :] = positions
     return v
+
+
+class ReferenceRpoly:
+    """The reference's own Jenkins-Traub root finder (oracle/_ref/librpoly_ref.so, built by
+    oracle/Makefile from /root/reference/.../src/rpoly.cpp).  Not re-entrant.  TEST USE ONLY."""
+
+    PATH = os.path.join(_HERE, "_ref", "librpoly_ref.so")
+
+    @classmethod
+    def available(cls):
+        if not os.path.exists(cls.PATH) and os.path.exists("/root/reference/mav_trajectory_generation/src/rpoly.cpp"):
+            subprocess.call(["make", "-C", _HERE, "-s", "ref"])
+        return os.path.exists(cls.PATH)
+
+    def __init__(self):
+        assert self.available()
+        self.lib = C.CDLL(self.PATH)
+
+    def roots_increasing(self, coeffs_increasing):
+        """ref findRootsJenkinsTraub(VectorXd increasing, VectorXcd*) -> complex roots or None."""
+        c = np.ascontiguousarray(np.asarray(coeffs_increasing, np.float64))
+        re = np.zeros(len(c) + 1)
+        im = np.zeros(len(c) + 1)
+        n = self.lib.ref_rpoly_increasing(c.ctypes.data_as(C.c_void_p), len(c), re.ctypes.data_as(C.c_void_p),
+                                          im.ctypes.data_as(C.c_void_p))
+        if n < 0:
+            return None
+        return re[:n] + 1j * im[:n]
+
+    def real_roots_in_range(self, coeffs_increasing, t0, t1):
+        """Selection rule of the reference (LIN.i:423-434 / src/polynomial.cpp:41-52)."""
+        r = self.roots_increasing(coeffs_increasing)
+        if r is None:
+            return None
+        keep = [z.real for z in r if abs(z.imag) <= np.finfo(np.float64).eps and t0 <= z.real <= t1]
+        return np.array(sorted(keep))
