@@ -17,9 +17,12 @@
 // the real roots in range.  Here every thread owns one segment and isolates the real roots
 // directly: the real roots of g^(m+1) split [0, T] into intervals on which g^(m) is monotone, so
 // each sign change brackets exactly one root, refined by a safeguarded Newton iteration; the
-// recursion starts at the linear derivative.  No complex arithmetic, no deflation, fixed-size
-// state (4 arrays of <= 24 doubles), and every thread of a warp runs the same level at the same
-// time.  A second kernel folds the per-segment results in the reference's candidate order.
+// recursion starts at the linear derivative.  No complex arithmetic, no deflation.  The kernel is
+// a template over the length of g and the recursion level, so g and the coefficients of the
+// current level live in registers and every Horner step is two DFMA with no memory access; all
+// threads of a warp are at the same level at the same time (FP64-pipe bound, divergence only in
+// the number of brackets and Newton steps).  A second kernel folds the per-segment results in
+// the reference's candidate order.
 #include <cfloat>
 
 #include "minsnap_device.cuh"
@@ -29,41 +32,58 @@ namespace minsnap {
 
 namespace {
 
-constexpr int kMaxG = 24;  // coefficients of g: 2N - 2k - 2 <= 22 for N <= 12
+constexpr int kMaxG = 22;  // coefficients of g: 2N - 2k - 2 <= 22 for N <= 12
 
 struct SegmentExtremum {
   double max_t, max_v, min_t, min_v;
 };
 
-// C(i, m) for i < 24: derivative level m of g divided by m! has coefficients C(j+m, m) g[j+m].
-__constant__ double c_binomial[kMaxG][kMaxG];
+// C(i, m): derivative level m of g divided by m! has coefficients C(j+m, m) g[j+m].  Every
+// intermediate value is an integer below 2^53, so the result is exact.
+__host__ __device__ constexpr double binomial(int i, int m) {
+  double c = 1.0;
+  for (int q = 1; q <= m; ++q) c = c * (double)(i - m + q) / (double)q;
+  return c;
+}
 
-struct PolyView {
-  const double* d;
-  int deg;
-  __device__ __forceinline__ void eval(double t, double& f, double& fp) const {
-    double a = d[deg], b = 0.0;
-    for (int j = deg - 1; j >= 0; --j) {
-      b = fma(b, t, a);
-      a = fma(a, t, d[j]);
-    }
-    f = a;
-    fp = b;
-  }
-  __device__ __forceinline__ double value(double t) const {
-    double a = d[deg];
-    for (int j = deg - 1; j >= 0; --j) a = fma(a, t, d[j]);
-    return a;
-  }
-};
+// Horner evaluations with compile-time degree: the coefficients stay in registers.
+template <int DEG>
+__device__ __forceinline__ double poly_value(const double (&d)[DEG + 1], double t) {
+  double a = d[DEG];
+#pragma unroll
+  for (int j = DEG - 1; j >= 0; --j) a = fma(a, t, d[j]);
+  return a;
+}
 
-// One root of a monotone piece: f(lo) and f(hi) have opposite signs.
-__device__ double refine_bracket(const PolyView& p, double lo, double hi, bool lo_negative) {
+// Value, slope and a running bound of the rounding error of the value (Horner with
+// e <- e |t| + |a|; the computed value differs from the exact one by at most ~eps * e).
+template <int DEG>
+__device__ __forceinline__ void poly_value_slope_bound(const double (&d)[DEG + 1], double t, double& f, double& fp,
+                                                       double& e) {
+  const double at = fabs(t);
+  double a = d[DEG], b = 0.0, err = fabs(a);
+#pragma unroll
+  for (int j = DEG - 1; j >= 0; --j) {
+    b = fma(b, t, a);
+    a = fma(a, t, d[j]);
+    err = fma(err, at, fabs(a));
+  }
+  f = a;
+  fp = b;
+  e = err;
+}
+
+// One root of a monotone piece: f(lo) and f(hi) have opposite signs.  Newton from the midpoint,
+// bisection whenever the step leaves the bracket; stops when |f| is inside its own rounding error
+// (nothing more can be learnt from the sign of f), when the step no longer changes x, or when
+// the bracket has collapsed.
+template <int DEG>
+__device__ __forceinline__ double refine_bracket(const double (&d)[DEG + 1], double lo, double hi, bool lo_negative) {
   double x = 0.5 * (lo + hi);
   for (int it = 0; it < 128; ++it) {
-    double f, fp;
-    p.eval(x, f, fp);
-    if (f == 0.0) return x;
+    double f, fp, e;
+    poly_value_slope_bound<DEG>(d, x, f, fp, e);
+    if (fabs(f) <= DBL_EPSILON * e) return x;
     if ((f < 0.0) == lo_negative) lo = x; else hi = x;
     double next = fp != 0.0 ? x - f / fp : lo - 1.0;
     if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);
@@ -74,36 +94,64 @@ __device__ double refine_bracket(const PolyView& p, double lo, double hi, bool l
   return x;
 }
 
-// Real roots of g (n coefficients, increasing, g[n-1] != 0) inside [t0, t1], ascending.
-// prev/cur/d: scratch of kMaxG doubles each.  Returns the count; the roots are in `prev`.
-__device__ int real_roots_in_range(const double* g, int n, double t0, double t1, double* prev, double* cur,
-                                   double* d) {
-  const int deg = n - 1;
-  int n_prev = 0;
-  for (int m = deg - 1; m >= 0; --m) {
-    const int dm = deg - m;
-    for (int j = 0; j <= dm; ++j) d[j] = c_binomial[j + m][m] * g[j + m];
-    const PolyView p{d, dm};
-    int n_cur = 0;
-    double left = t0;
-    double f_left = p.value(left);
-    if (f_left == 0.0) cur[n_cur++] = left;
-    for (int i = 0; i <= n_prev; ++i) {
-      const double right = i < n_prev ? prev[i] : t1;
-      if (!(right > left)) continue;
-      const double f_right = p.value(right);
-      if (f_right == 0.0) {
-        cur[n_cur++] = right;
-      } else if (f_left != 0.0 && (f_left < 0.0) != (f_right < 0.0)) {
-        cur[n_cur++] = refine_bracket(p, left, right, f_left < 0.0);
-      }
-      left = right;
-      f_left = f_right;
+// Level M of the recursion: the real roots of g^(M) inside [t0, t1] (written to `cur`, ascending;
+// returns how many), given those of g^(M+1) in `prev`.  The level index is a template parameter
+// so that every coefficient index is a compile-time constant and g stays in registers; all
+// threads of a warp are at the same level at the same time.
+template <int LEN, int M>
+__device__ __noinline__ int root_level(const double (&g)[LEN], double t0, double t1, const double* prev, int n_prev,
+                                       double* cur) {
+  constexpr int DEG = LEN - 1 - M;
+  double d[DEG + 1];
+#pragma unroll
+  for (int j = 0; j <= DEG; ++j) d[j] = binomial(j + M, M) * g[j + M];
+  int n_cur = 0;
+  double left = t0;
+  double f_left = poly_value<DEG>(d, left);
+  if (f_left == 0.0) cur[n_cur++] = left;
+  for (int i = 0; i <= n_prev; ++i) {
+    const double right = i < n_prev ? prev[i] : t1;
+    if (!(right > left)) continue;
+    const double f_right = poly_value<DEG>(d, right);
+    if (f_right == 0.0) {
+      cur[n_cur++] = right;
+    } else if (f_left != 0.0 && (f_left < 0.0) != (f_right < 0.0)) {
+      cur[n_cur++] = refine_bracket<DEG>(d, left, right, f_left < 0.0);
     }
-    for (int i = 0; i < n_cur; ++i) prev[i] = cur[i];
-    n_prev = n_cur;
+    left = right;
+    f_left = f_right;
   }
-  return n_prev;
+  return n_cur;
+}
+
+template <int LEN, int M>
+__device__ __forceinline__ int dispatch_level(int m, const double (&g)[LEN], double t0, double t1, const double* prev,
+                                              int n_prev, double* cur) {
+  if (m == M) return root_level<LEN, M>(g, t0, t1, prev, n_prev, cur);
+  if constexpr (M > 0) return dispatch_level<LEN, M - 1>(m, g, t0, t1, prev, n_prev, cur);
+  return 0;
+}
+
+// Real roots of g inside [t0, t1]; coefficients above index `last` are zero (removed trailing
+// coefficients): the levels whose polynomial would be constant are skipped.  Returns the buffer
+// that holds the roots.
+template <int LEN>
+__device__ __forceinline__ const double* real_roots(const double (&g)[LEN], int last, double t0, double t1,
+                                                    double* buf_a, double* buf_b, int& n_roots) {
+  double* prev = buf_a;
+  double* cur = buf_b;
+  int n_prev = 0;
+  // every thread walks all levels so that a warp stays at one level; a level above the thread's
+  // own degree is skipped by predicate
+  for (int m = LEN - 2; m >= 0; --m) {
+    if (m > last - 1) continue;
+    n_prev = dispatch_level<LEN, LEN - 2>(m, g, t0, t1, prev, n_prev, cur);
+    double* swap = prev;
+    prev = cur;
+    cur = swap;
+  }
+  n_roots = n_prev;
+  return prev;
 }
 
 struct ExtremaParams {
@@ -140,6 +188,10 @@ __device__ inline double magnitude_at(const double* seg, int D, int N, uint32_t 
   return sqrt(s);
 }
 
+// One thread per segment.  LEN (even) is the smallest instantiated size that holds the candidate
+// polynomial; shorter polynomials are padded with zero coefficients, which the removal of
+// trailing coefficients then treats like the reference's own zeros.
+template <int LEN>
 __global__ void __launch_bounds__(128) segment_extrema_kernel(ExtremaParams p) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.B * p.K) return;
@@ -148,23 +200,27 @@ __global__ void __launch_bounds__(128) segment_extrema_kernel(ExtremaParams p) {
   const double T = p.times[idx];
   const int n_dims = __popc(p.dim_mask);
 
-  double g[kMaxG], d[kMaxG], ra[kMaxG], rb[kMaxG];
-  int len;
-  const int n_d = N - k, n_dd = n_d - 1;
+  double g[LEN];
+#pragma unroll
+  for (int i = 0; i < LEN; ++i) g[i] = 0.0;
   if (n_dims > 1) {
     // g = sum over dimensions of convolve(d, dd) (ref LIN.i:396-404 / src/segment.cpp:103-112);
     // convolve sums kernel[j] data[i-j] from the highest j down (src/polynomial.cpp:164-172).
-    len = n_d + n_dd - 1;
-    for (int i = 0; i < len; ++i) g[i] = 0.0;
+    constexpr int ND = LEN / 2 + 1, NDD = LEN / 2;   // LEN = ND + NDD - 1
     for (int dim = 0; dim < D; ++dim) {
       if (!((p.dim_mask >> dim) & 1u)) continue;
       const double* c = seg + dim * N;
-      for (int j = 0; j < n_d; ++j) ra[j] = c[j + k] * falling_factorial(k, j + k);             // d
-      for (int j = 0; j < n_dd; ++j) rb[j] = c[j + k + 1] * falling_factorial(k + 1, j + k + 1); // dd
-      for (int i = 0; i < len; ++i) {
-        const int j_hi = min(n_dd - 1, i), j_lo = max(0, i - (n_d - 1));
+      double pd[ND], pdd[NDD];
+#pragma unroll
+      for (int j = 0; j < ND; ++j) pd[j] = j + k < N ? c[j + k] * falling_factorial(k, j + k) : 0.0;
+#pragma unroll
+      for (int j = 0; j < NDD; ++j) pdd[j] = j + k + 1 < N ? c[j + k + 1] * falling_factorial(k + 1, j + k + 1) : 0.0;
+#pragma unroll
+      for (int i = 0; i < LEN; ++i) {
         double acc = 0.0;
-        for (int j = j_hi; j >= j_lo; --j) acc += rb[j] * ra[i - j];
+#pragma unroll
+        for (int j = NDD - 1; j >= 0; --j)
+          if (j <= i && i - j < ND) acc += pdd[j] * pd[i - j];
         g[i] += acc;
       }
     }
@@ -173,21 +229,26 @@ __global__ void __launch_bounds__(128) segment_extrema_kernel(ExtremaParams p) {
     int dim = 0;
     while (dim < D - 1 && !((p.dim_mask >> dim) & 1u)) ++dim;
     const double* c = seg + dim * N;
-    len = n_dd;
-    for (int j = 0; j < n_dd; ++j) g[j] = c[j + k + 1] * falling_factorial(k + 1, j + k + 1);
+#pragma unroll
+    for (int j = 0; j < LEN; ++j) g[j] = j + k + 1 < N ? c[j + k + 1] * falling_factorial(k + 1, j + k + 1) : 0.0;
   }
   // ref src/rpoly.cpp:44-55: drop trailing coefficients below machine epsilon.  The threshold is
   // absolute, so on long segments (T above ~12 s) the reference truncates coefficients that
   // matter near t = T; reproduced by default, keep_small removes exact zeros only.
-  int last = len - 1;
-  if (p.keep_small) {
-    while (last >= 0 && g[last] == 0.0) --last;
-  } else {
-    while (last >= 0 && !(fabs(g[last]) >= DBL_EPSILON)) --last;
+  int last = -1;
+#pragma unroll
+  for (int i = 0; i < LEN; ++i) {
+    const bool keep = p.keep_small ? g[i] != 0.0 : fabs(g[i]) >= DBL_EPSILON;
+    if (keep) last = i;
   }
+#pragma unroll
+  for (int i = 0; i < LEN; ++i)
+    if (i > last) g[i] = 0.0;
+
+  double buf_a[LEN], buf_b[LEN];
   int n_roots = 0;
-  if (last >= 1 && T >= 0.0) n_roots = real_roots_in_range(g, last + 1, 0.0, T, ra, rb, d);
-  const double* roots = ra;
+  const double* roots = buf_a;
+  if (last >= 1 && T >= 0.0) roots = real_roots<LEN>(g, last, 0.0, T, buf_a, buf_b, n_roots);
 
   if (p.root_count) p.root_count[idx] = n_roots;
   if (p.root_times)
@@ -253,20 +314,11 @@ __global__ void __launch_bounds__(128) fold_extrema_kernel(FoldParams p) {
   }
 }
 
-cudaError_t upload_binomials() {
-  static cudaError_t status = [] {
-    static double h[kMaxG][kMaxG];
-    for (int i = 0; i < kMaxG; ++i)
-      for (int m = 0; m < kMaxG; ++m) {
-        if (m > i) { h[i][m] = 0.0; continue; }
-        // exact in double: C(23, 11) = 1,352,078
-        double c = 1.0;
-        for (int q = 1; q <= m; ++q) c = c * (double)(i - m + q) / (double)q;
-        h[i][m] = c;
-      }
-    return cudaMemcpyToSymbol(c_binomial, h, sizeof(h));
-  }();
-  return status;
+template <int LEN>
+cudaError_t launch_segments(const ExtremaParams& p, cudaStream_t stream) {
+  const long n = p.B * p.K;
+  segment_extrema_kernel<LEN><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -279,8 +331,9 @@ int extrema_max_roots(int N, int derivative, int n_dims) {
 
 cudaError_t launch_extrema(const ExtremaArgs& a, cudaStream_t stream) {
   if (a.B == 0) return cudaSuccess;
-  cudaError_t e = upload_binomials();
-  if (e != cudaSuccess) return e;
+  const int len = extrema_max_roots(a.N, a.derivative, __builtin_popcount(a.dim_mask)) + 1;
+  if (len > kMaxG) return cudaErrorInvalidValue;
+  cudaError_t e;
   void* scratch = nullptr;
   if ((e = cudaMallocAsync(&scratch, sizeof(SegmentExtremum) * (size_t)a.B * a.K, stream)) != cudaSuccess) return e;
   ExtremaParams p;
@@ -290,9 +343,16 @@ cudaError_t launch_extrema(const ExtremaArgs& a, cudaStream_t stream) {
   p.coeffs = a.d_coeffs; p.times = a.d_times;
   p.per_segment = static_cast<SegmentExtremum*>(scratch);
   p.root_times = a.d_root_times; p.root_count = a.d_root_count; p.max_roots = a.max_roots;
-  const long n = a.B * a.K;
-  segment_extrema_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p);
-  e = cudaGetLastError();
+  e = len <= 4    ? launch_segments<4>(p, stream)
+      : len <= 6  ? launch_segments<6>(p, stream)
+      : len <= 8  ? launch_segments<8>(p, stream)
+      : len <= 10 ? launch_segments<10>(p, stream)
+      : len <= 12 ? launch_segments<12>(p, stream)
+      : len <= 14 ? launch_segments<14>(p, stream)
+      : len <= 16 ? launch_segments<16>(p, stream)
+      : len <= 18 ? launch_segments<18>(p, stream)
+      : len <= 20 ? launch_segments<20>(p, stream)
+                  : launch_segments<22>(p, stream);
   if (e == cudaSuccess) {
     FoldParams f;
     f.B = a.B; f.K = a.K; f.mode = a.mode; f.per_segment = p.per_segment;

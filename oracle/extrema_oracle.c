@@ -126,22 +126,26 @@ static int last_nonzero(const real* c, int n, int keep_small) {
 API int orc_last_nonzero_coefficient(const real* c, int n) { return last_nonzero(c, n, 0); }
 
 /* ---- real roots of a polynomial inside [t0, t1] ----------------------------------------- */
-static void eval_pair(const xreal* d, int deg, xreal t, xreal* f, xreal* fp) {
-  xreal a = d[deg], b = 0;
+/* value, slope and a running bound of the rounding error of the value */
+static void eval_pair(const xreal* d, int deg, xreal t, xreal* f, xreal* fp, xreal* bound) {
+  const xreal at = fabsl(t);
+  xreal a = d[deg], b = 0, e = fabsl(a);
   for (int j = deg - 1; j >= 0; --j) {
     b = b * t + a;
     a = a * t + d[j];
+    e = e * at + fabsl(a);
   }
   *f = a;
   *fp = b;
+  if (bound) *bound = 2 * LDBL_EPSILON * e;
 }
 
 static xreal refine_bracket(const xreal* d, int deg, xreal lo, xreal hi, int lo_negative) {
   xreal x = 0.5L * (lo + hi);
   for (int it = 0; it < 300; ++it) {
-    xreal f, fp;
-    eval_pair(d, deg, x, &f, &fp);
-    if (f == 0) return x;
+    xreal f, fp, bound;
+    eval_pair(d, deg, x, &f, &fp, &bound);
+    if (fabsl(f) <= bound) return x; /* inside the rounding error of the evaluation */
     if ((f < 0) == lo_negative) lo = x; else hi = x;
     xreal next = fp != 0 ? x - f / fp : lo - 1;
     if (!(next > lo && next < hi)) next = 0.5L * (lo + hi);
@@ -172,13 +176,13 @@ API int orc_real_roots_in_range(const real* g, int n, real t0_in, real t1_in, re
     int n_cur = 0;
     /* separators: t0, the roots of g^(m+1) strictly inside, t1 */
     xreal left = t0, f_left, tmp;
-    eval_pair(d, dm, left, &f_left, &tmp);
+    eval_pair(d, dm, left, &f_left, &tmp, 0);
     if (f_left == 0) cur[n_cur++] = left;
     for (int i = 0; i <= n_prev; ++i) {
       const xreal right = i < n_prev ? prev[i] : t1;
       if (!(right > left)) continue;
       xreal f_right;
-      eval_pair(d, dm, right, &f_right, &tmp);
+      eval_pair(d, dm, right, &f_right, &tmp, 0);
       if (f_right == 0) {
         cur[n_cur++] = right;
       } else if (f_left != 0 && (f_left < 0) != (f_right < 0)) {
