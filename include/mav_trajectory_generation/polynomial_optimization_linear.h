@@ -11,8 +11,9 @@
 //   setupMappingMatrix / invertMappingMatrix / computeQuadraticCostJacobian / getA / getAInverse /
 //   getR                -> minsnap_segment_matrices_host           (ref LIN.i:101-169, 573-589)
 //
-// Not provided (out of the hot path, need the rpoly root finder): the
-// computeSegmentMaximumMagnitudeCandidates* / computeMaximumOfMagnitude members.
+//   computeMaximumOfMagnitude / computeSegmentMaximumMagnitudeCandidates
+//                       -> minsnap_extrema_host                    (ref LIN.i:378-503; the real roots are
+//                          isolated on the GPU instead of by the reference's Jenkins-Traub routine)
 // Additive: PolynomialOptimizationBatch<N> below solves many independent problems per call.
 #ifndef MAV_TRAJECTORY_GENERATION_POLYNOMIAL_OPTIMIZATION_LINEAR_H_
 #define MAV_TRAJECTORY_GENERATION_POLYNOMIAL_OPTIMIZATION_LINEAR_H_
@@ -21,6 +22,7 @@
 #include <ostream>
 #include <vector>
 
+#include "mav_trajectory_generation/extremum.h"
 #include "mav_trajectory_generation/minsnap_gpu.h"
 #include "mav_trajectory_generation/motion_defines.h"
 #include "mav_trajectory_generation/polynomial.h"
@@ -135,6 +137,107 @@ class PolynomialOptimization {
                                  derivative_to_optimize_, coeffs.data(), segment_times_.data(), &cost),
                "minsnap_cost_host");
     return cost;
+  }
+
+  // ---- extrema of |p^(Derivative)| (ref LIN.i:378-503) ---------------------------------------------
+  // Appends to `candidates` the times inside [t_start, t_stop] (t_start >= 0) at which the magnitude of
+  // the derivative may be extremal: the real roots of sum_dim p^(k) p^(k+1), or of p^(k+1) for one
+  // dimension, in ascending order.
+  template <int Derivative>
+  static bool computeSegmentMaximumMagnitudeCandidates(const Segment& segment, double t_start, double t_stop,
+                                                       std::vector<double>* candidates) {
+    CHECK(candidates);
+    static_assert(N - Derivative - 1 > 0, "N-Derivative-1 has to be greater 0");
+    CHECK_EQ(segment.N(), static_cast<int>(N));
+    CHECK_GE(t_start, 0.0) << "the candidate search runs over [0, t_stop]";
+    if (t_start > t_stop) return true;
+    const int D = segment.D();
+    std::vector<double> coeffs = segment.packCoefficients();
+    const int max_roots = minsnap_extrema_max_roots(N, Derivative, D);
+    std::vector<double> times(max_roots + 2);
+    int32_t n_roots = 0;
+    gpu::check(minsnap_extrema_host(1, 1, D, N, coeffs.data(), &t_stop, Derivative,
+                                    gpu::extremaMode(MINSNAP_EXTREMA_OPTIMIZATION), 0, nullptr, nullptr, nullptr, nullptr,
+                                    nullptr, nullptr, times.data(), nullptr, &n_roots),
+               "minsnap_extrema_host");
+    for (int i = 0; i < n_roots; ++i)
+      if (times[2 + i] >= t_start) candidates->push_back(times[2 + i]);
+    return true;
+  }
+
+  // The same candidates found by sampling every dt and watching the squared magnitude turn around
+  // (ref LIN.i:439-468); the samples are evaluated on the GPU in one launch.
+  template <int Derivative>
+  static void computeSegmentMaximumMagnitudeCandidatesBySampling(const Segment& segment, double t_start, double t_stop,
+                                                                 double dt, std::vector<double>* candidates) {
+    CHECK(candidates);
+    CHECK_GT(dt, 0.0);
+    std::vector<double> ts;
+    ts.push_back(t_start - dt);
+    ts.push_back(t_start);
+    for (double t = t_start + dt; t < t_stop + 2 * dt; t += dt) ts.push_back(t);
+    const std::vector<double> samples = segment.evaluateBatch(ts, Derivative + 1);
+    const int D = segment.D();
+    auto squared_norm = [&](size_t m) {
+      double s = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double v = samples[(m * (Derivative + 1) + Derivative) * D + d];
+        s += v * v;
+      }
+      return s;
+    };
+    auto sgn = [](double x) { return (0.0 < x) - (x < 0.0); };
+    double value_old = squared_norm(1);
+    double direction = value_old - squared_norm(0);
+    for (size_t m = 2; m < ts.size(); ++m) {
+      const double value_new = squared_norm(m);
+      const double direction_new = value_new - value_old;
+      if (sgn(direction) != sgn(direction_new)) candidates->push_back(ts[m] - dt);
+      value_old = value_new;
+      direction = direction_new;
+    }
+  }
+
+  // Largest magnitude of the derivative over the solved trajectory: per segment its start and the
+  // candidate times above, plus the end of the last segment; a candidate replaces the incumbent
+  // only when strictly larger; `candidates`, when given, receives every candidate in that order.
+  template <int Derivative>
+  Extremum computeMaximumOfMagnitude(std::vector<Extremum>* candidates) const {
+    static_assert(N - Derivative - 1 > 0, "N-Derivative-1 has to be greater 0");
+    if (candidates != nullptr) candidates->clear();
+    Extremum extremum;
+    if (n_segments_ == 0) return extremum;
+    CHECK(n_segments_ == segments_.size());
+    const int K = static_cast<int>(n_segments_), D = static_cast<int>(dimension_);
+    std::vector<double> coeffs = packCoefficients();
+    std::vector<double> durations(n_segments_);
+    for (size_t i = 0; i < n_segments_; ++i) durations[i] = segments_[i].getTime();
+    const int stride = minsnap_extrema_max_roots(N, Derivative, D) + 2;
+    std::vector<double> times, values;
+    std::vector<int32_t> counts;
+    if (candidates != nullptr) {
+      times.resize(static_cast<size_t>(K) * stride);
+      values.resize(static_cast<size_t>(K) * stride);
+      counts.resize(n_segments_);
+    }
+    int32_t segment_idx = 0;
+    gpu::check(minsnap_extrema_host(1, K, D, N, coeffs.data(), durations.data(), Derivative,
+                                    gpu::extremaMode(MINSNAP_EXTREMA_OPTIMIZATION), 0, &extremum.time, &extremum.value,
+                                    &segment_idx, nullptr, nullptr, nullptr,
+                                    candidates ? times.data() : nullptr, candidates ? values.data() : nullptr,
+                                    candidates ? counts.data() : nullptr),
+               "minsnap_extrema_host");
+    extremum.segment_idx = segment_idx;
+    if (candidates != nullptr) {
+      for (int s = 0; s < K; ++s) {
+        const double* t = &times[static_cast<size_t>(s) * stride];
+        const double* v = &values[static_cast<size_t>(s) * stride];
+        candidates->emplace_back(t[0], v[0], s);
+        for (int i = 0; i < counts[s]; ++i) candidates->emplace_back(t[2 + i], v[2 + i], s);
+        if (s == K - 1) candidates->emplace_back(t[1], v[1], s);
+      }
+    }
+    return extremum;
   }
 
   void updateSegmentTimes(const std::vector<double>& segment_times) {

@@ -1,12 +1,15 @@
 // Segment: D polynomials sharing one duration (mirror of ref include/mav_trajectory_generation/
-// segment.h:43-119, src/segment.cpp:27-80; the extremum members are out of scope).
+// segment.h:43-119, src/segment.cpp:27-199).
 #ifndef MAV_TRAJECTORY_GENERATION_SEGMENT_H_
 #define MAV_TRAJECTORY_GENERATION_SEGMENT_H_
 
+#include <cmath>
 #include <cstdint>
+#include <limits>
 #include <ostream>
 #include <vector>
 
+#include "mav_trajectory_generation/extremum.h"
 #include "mav_trajectory_generation/motion_defines.h"
 #include "mav_trajectory_generation/polynomial.h"
 
@@ -74,7 +77,111 @@ class Segment {
     return out;
   }
 
+  // ---- extrema of the magnitude of a derivative over [t_start, t_end] (ref src/segment.cpp:82-199) ----
+  // Candidate times: t_start, t_end, then the real roots inside the range of d/dt |p^(derivative)|^2
+  // (one dimension: of p^(derivative+1)), ascending.  The roots are isolated on the GPU
+  // (minsnap_extrema_host) instead of by the reference's Jenkins-Traub routine.  t_start >= 0.
+  bool computeMinMaxMagnitudeCandidateTimes(int derivative, double t_start, double t_end,
+                                            const std::vector<int>& dimensions,
+                                            std::vector<double>* candidate_times) const {
+    CHECK_NOTNULL(candidate_times);
+    std::vector<Extremum> candidates;
+    candidate_times->clear();
+    if (!computeMinMaxMagnitudeCandidates(derivative, t_start, t_end, dimensions, &candidates)) return false;
+    for (const Extremum& c : candidates) candidate_times->push_back(c.time);
+    return true;
+  }
+
+  bool computeMinMaxMagnitudeCandidates(int derivative, double t_start, double t_end,
+                                        const std::vector<int>& dimensions,
+                                        std::vector<Extremum>* candidates) const {
+    CHECK_NOTNULL(candidates);
+    candidates->clear();
+    if (dimensions.empty()) {
+      LOG(WARNING) << "No dimensions specified." << std::endl;
+      return false;
+    }
+    uint32_t mask = 0;
+    if (!gpu::dimensionMask(dimensions, D_, &mask)) {
+      LOG(WARNING) << "Specified dimensions are out of bounds [0.." << D_ - 1 << "]." << std::endl;
+      return false;
+    }
+    if (N_ - derivative - 1 < 0) {
+      LOG(WARNING) << "N - derivative - 1 has to be at least 0.";
+      return false;
+    }
+    if (t_start > t_end) {
+      LOG(WARNING) << "t_start is greater than t_end.";
+      return false;
+    }
+    CHECK_GE(t_start, 0.0) << "the candidate search runs over [0, t_end]";
+    std::vector<double> coeffs = packCoefficients();
+    const int n_dims = __builtin_popcount(mask);
+    const int max_roots = derivative <= N_ - 2 ? minsnap_extrema_max_roots(N_, derivative, n_dims) : 0;
+    std::vector<double> times(max_roots + 2), values(max_roots + 2);
+    int32_t n_roots = 0;
+    if (derivative <= N_ - 2) {
+      gpu::check(minsnap_extrema_host(1, 1, D_, N_, coeffs.data(), &t_end, derivative,
+                                      gpu::extremaMode(MINSNAP_EXTREMA_TRAJECTORY), mask, nullptr, nullptr, nullptr,
+                                      nullptr, nullptr, nullptr, times.data(), values.data(), &n_roots),
+                 "minsnap_extrema_host");
+    } else {
+      times[1] = t_end;   // the highest derivative is a constant: no roots, the range ends only
+      values[0] = values[1] = magnitude(t_end, derivative, dimensions);
+    }
+    candidates->reserve(static_cast<size_t>(n_roots) + 2);
+    candidates->emplace_back(t_start, t_start == 0.0 ? values[0] : magnitude(t_start, derivative, dimensions), 0);
+    candidates->emplace_back(t_end, values[1], 0);
+    for (int i = 0; i < n_roots; ++i)
+      if (times[2 + i] >= t_start) candidates->emplace_back(times[2 + i], values[2 + i], 0);
+    return true;
+  }
+
+  bool selectMinMaxMagnitudeFromCandidates(double t_start, double t_end, int derivative,
+                                           const std::vector<int>& dimensions,
+                                           const std::vector<Extremum>& candidates, Extremum* minimum,
+                                           Extremum* maximum) const {
+    CHECK_NOTNULL(minimum);
+    CHECK_NOTNULL(maximum);
+    if (t_start > t_end) {
+      LOG(WARNING) << "t_start is greater than t_end.";
+      return false;
+    }
+    minimum->value = std::numeric_limits<double>::max();
+    maximum->value = std::numeric_limits<double>::lowest();
+    for (const Extremum& candidate : candidates) {
+      if (candidate.time < t_start || candidate.time > t_end) continue;
+      if (*maximum < candidate) *maximum = candidate;
+      if (candidate < *minimum) *minimum = candidate;
+    }
+    const Extremum ends[2] = {Extremum(t_start, magnitude(t_start, derivative, dimensions), 0),
+                              Extremum(t_end, magnitude(t_end, derivative, dimensions), 0)};
+    for (const Extremum& e : ends) {
+      if (*maximum < e) *maximum = e;
+      if (e < *minimum) *minimum = e;
+    }
+    return true;
+  }
+
+  // coefficients [D][N] in the C-ABI layout
+  std::vector<double> packCoefficients() const {
+    std::vector<double> coeffs(static_cast<size_t>(D_) * N_);
+    for (int d = 0; d < D_; ++d) {
+      const Eigen::VectorXd c = polynomials_[d].getCoefficients(0);
+      for (int j = 0; j < N_; ++j) coeffs[static_cast<size_t>(d) * N_ + j] = c[j];
+    }
+    return coeffs;
+  }
+
  protected:
+  // sqrt of the sum over the listed dimensions of p^(derivative)(t)^2 (evaluated on the GPU)
+  double magnitude(double t, int derivative, const std::vector<int>& dimensions) const {
+    const Eigen::VectorXd v = evaluate(t, derivative);
+    double s = 0.0;
+    for (int dim : dimensions) s += v[dim] * v[dim];
+    return std::sqrt(s);
+  }
+
   Polynomial::Vector polynomials_;
   double time_;
 

@@ -4,8 +4,10 @@
 #ifndef MAV_TRAJECTORY_GENERATION_TRAJECTORY_H_
 #define MAV_TRAJECTORY_GENERATION_TRAJECTORY_H_
 
+#include <limits>
 #include <vector>
 
+#include "mav_trajectory_generation/extremum.h"
 #include "mav_trajectory_generation/segment.h"
 
 namespace mav_trajectory_generation {
@@ -111,6 +113,43 @@ class Trajectory {
                "minsnap_sample_at_host");
     if (segment_index) *segment_index = seg;
     return out;
+  }
+
+  // Minimum and maximum of the magnitude of a derivative over the listed dimensions and the whole
+  // trajectory (ref src/trajectory.cpp:181-217): per segment the candidates are its start, its end
+  // and the real roots of d/dt |p^(derivative)|^2 inside it; the first strictly smaller / larger
+  // candidate wins.  One GPU call for all segments (minsnap_extrema_host).
+  bool computeMinMaxMagnitude(int derivative, const std::vector<int>& dimensions, Extremum* minimum,
+                              Extremum* maximum) const {
+    CHECK_NOTNULL(minimum);
+    CHECK_NOTNULL(maximum);
+    minimum->value = std::numeric_limits<double>::max();
+    maximum->value = std::numeric_limits<double>::lowest();
+    if (segments_.empty()) return true;
+    if (dimensions.empty()) {
+      LOG(WARNING) << "No dimensions specified." << std::endl;
+      return false;
+    }
+    uint32_t mask = 0;
+    if (!gpu::dimensionMask(dimensions, D_, &mask)) {
+      LOG(WARNING) << "Specified dimensions are out of bounds [0.." << D_ - 1 << "]." << std::endl;
+      return false;
+    }
+    if (derivative < 0 || N_ - derivative - 2 < 0) {
+      LOG(WARNING) << "N - derivative - 1 has to be at least 0.";
+      return false;
+    }
+    std::vector<double> coeffs, durations;
+    pack(&coeffs, &durations);
+    int32_t min_segment = 0, max_segment = 0;
+    gpu::check(minsnap_extrema_host(1, K(), D_, N_, coeffs.data(), durations.data(), derivative,
+                                    gpu::extremaMode(MINSNAP_EXTREMA_TRAJECTORY), mask, &maximum->time,
+                                    &maximum->value, &max_segment, &minimum->time, &minimum->value, &min_segment,
+                                    nullptr, nullptr, nullptr),
+               "minsnap_extrema_host");
+    minimum->segment_idx = min_segment;
+    maximum->segment_idx = max_segment;
+    return true;
   }
 
   // Samples one derivative from t_start to t_end every dt, accumulating the sample time the way

@@ -197,8 +197,10 @@ MINSNAP_API int minsnap_cost_sweep(long B, int S, int K, int D, int N, int deriv
  * removed and the result agrees with dense sampling.
  * dim_mask: bit d set => dimension d takes part; 0 => all D dimensions (D <= 32).
  * Times are relative to the start of the reported segment, as in the reference's Extremum.
- * Outputs [B] each, any may be NULL.  Optional d_root_times [B][K][max_roots] (ascending; max_roots
- * from minsnap_extrema_max_roots) and d_root_count [B][K]. */
+ * Outputs [B] each, any may be NULL.  Optional per-segment candidate lists in the order of
+ * Segment::computeMinMaxMagnitudeCandidates (start, end, then the roots, ascending):
+ * d_cand_times / d_cand_values [B][K][max_roots + 2] (max_roots from minsnap_extrema_max_roots;
+ * entries past 2 + count are not written) and d_root_count [B][K] = number of roots. */
 #define MINSNAP_EXTREMA_OPTIMIZATION 0
 #define MINSNAP_EXTREMA_TRAJECTORY 1
 #define MINSNAP_EXTREMA_KEEP_SMALL_COEFFICIENTS 16
@@ -207,7 +209,7 @@ MINSNAP_API int minsnap_extrema(long B, int K, int D, int N, const double* d_coe
                                 const double* d_times, int derivative, int mode, uint32_t dim_mask,
                                 double* d_max_time, double* d_max_value, int32_t* d_max_segment,
                                 double* d_min_time, double* d_min_value, int32_t* d_min_segment,
-                                double* d_root_times, int32_t* d_root_count,
+                                double* d_cand_times, double* d_cand_values, int32_t* d_root_count,
                                 minsnap_stream_t stream);
 
 /* ---- host-buffer entry points (synchronous; copies inside) -------------------------------
@@ -255,7 +257,8 @@ MINSNAP_API int minsnap_extrema_host(long B, int K, int D, int N, const double* 
                                      uint32_t dim_mask, double* h_max_time, double* h_max_value,
                                      int32_t* h_max_segment, double* h_min_time,
                                      double* h_min_value, int32_t* h_min_segment,
-                                     double* h_root_times, int32_t* h_root_count);
+                                     double* h_cand_times, double* h_cand_values,
+                                     int32_t* h_root_count);
 
 /* ---- a3: synthetic inputs (ref: createRandomVertices, src/vertex.cpp:27-79) -- HOST ONLY ----
  * positions[b] = vertex positions of createRandomVertices(., K, pos_min, pos_max, base_seed + b):

@@ -256,8 +256,9 @@ def extrema_max_roots(N, derivative, n_dims):
 
 def extrema(coeffs, times, derivative, mode=EXTREMA_OPTIMIZATION, dimensions=None, want_roots=False):
     """coeffs [B][K][D][N], times [B][K] (CUDA tensors) -> dict of [B] tensors: max_time, max_value,
-    max_segment (and min_* in EXTREMA_TRAJECTORY mode); with want_roots also root_times
-    [B][K][max_roots] and root_count [B][K].  Times are local to the reported segment."""
+    max_segment (and min_* in EXTREMA_TRAJECTORY mode); with want_roots also the per-segment
+    candidate lists cand_times / cand_values [B][K][max_roots + 2] (start, end, roots ascending),
+    root_count [B][K] and root_times (= cand_times[..., 2:]).  Times are local to the segment."""
     torch = _torch()
     B, K, D, N = coeffs.shape
     dev = coeffs.device
@@ -271,13 +272,17 @@ def extrema(coeffs, times, derivative, mode=EXTREMA_OPTIMIZATION, dimensions=Non
                  min_segment=torch.empty((B,), dtype=torch.int32, device=dev))
     if want_roots:
         mr = extrema_max_roots(N, derivative, bin(mask).count("1"))
-        r["root_times"] = torch.zeros((B, K, max(mr, 1)), dtype=torch.float64, device=dev)
+        r["cand_times"] = torch.zeros((B, K, mr + 2), dtype=torch.float64, device=dev)
+        r["cand_values"] = torch.zeros((B, K, mr + 2), dtype=torch.float64, device=dev)
         r["root_count"] = torch.empty((B, K), dtype=torch.int32, device=dev)
     capi.check(_lib().minsnap_extrema(B, K, D, N, _dptr(coeffs, torch.float64), _dptr(times, torch.float64),
                                       derivative, mode, mask, _dptr(r["max_time"]), _dptr(r["max_value"]),
                                       _dptr(r["max_segment"]), _dptr(r.get("min_time")), _dptr(r.get("min_value")),
-                                      _dptr(r.get("min_segment")), _dptr(r.get("root_times")),
-                                      _dptr(r.get("root_count")), _stream()), "minsnap_extrema")
+                                      _dptr(r.get("min_segment")), _dptr(r.get("cand_times")),
+                                      _dptr(r.get("cand_values")), _dptr(r.get("root_count")), _stream()),
+               "minsnap_extrema")
+    if want_roots:
+        r["root_times"] = r["cand_times"][:, :, 2:]
     return r
 
 
@@ -297,13 +302,17 @@ def extrema_host(coeffs, times, derivative, mode=EXTREMA_OPTIMIZATION, dimension
                  min_segment=np.empty((B,), np.int32))
     if want_roots:
         mr = extrema_max_roots(N, derivative, bin(mask).count("1"))
-        r["root_times"] = np.zeros((B, K, max(mr, 1)), np.float64)
+        r["cand_times"] = np.zeros((B, K, mr + 2), np.float64)
+        r["cand_values"] = np.zeros((B, K, mr + 2), np.float64)
         r["root_count"] = np.empty((B, K), np.int32)
     capi.check(_lib().minsnap_extrema_host(B, K, D, N, _hptr(coeffs), _hptr(times), derivative, mode, mask,
                                            _hptr(r["max_time"]), _hptr(r["max_value"]), _hptr(r["max_segment"]),
                                            _hptr(r.get("min_time")), _hptr(r.get("min_value")),
-                                           _hptr(r.get("min_segment")), _hptr(r.get("root_times")),
-                                           _hptr(r.get("root_count"))), "minsnap_extrema_host")
+                                           _hptr(r.get("min_segment")), _hptr(r.get("cand_times")),
+                                           _hptr(r.get("cand_values")), _hptr(r.get("root_count"))),
+               "minsnap_extrema_host")
+    if want_roots:
+        r["root_times"] = r["cand_times"][:, :, 2:]
     return r
 
 

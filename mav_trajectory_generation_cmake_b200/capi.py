@@ -35,8 +35,10 @@ SIGNATURES = {
     "minsnap_evaluate_range": (_i, [_l, _i, _i, _i, _vp, _vp, _d, _d, _d, _i, _i, _vp, _vp, _vp, _vp]),
     "minsnap_cost_sweep": (_i, [_l, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "minsnap_extrema_max_roots": (_i, [_i, _i, _i]),
-    "minsnap_extrema": (_i, [_l, _i, _i, _i, _vp, _vp, _i, _i, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "minsnap_extrema_host": (_i, [_l, _i, _i, _i, _vp, _vp, _i, _i, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "minsnap_extrema": (_i, [_l, _i, _i, _i, _vp, _vp, _i, _i, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _vp]),
+    "minsnap_extrema_host": (_i, [_l, _i, _i, _i, _vp, _vp, _i, _i, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp]),
     "minsnap_host_alloc": (_i, [_vp, _sz]),
     "minsnap_host_free": (_i, [_vp]),
     "minsnap_reorder_host": (_i, [_i, _i, _l, _vp, _vp, _vp]),

@@ -413,8 +413,8 @@ int minsnap_extrema_max_roots(int N, int derivative, int n_dims) {
 
 int minsnap_extrema(long B, int K, int D, int N, const double* d_coeffs, const double* d_times, int derivative,
                     int mode, uint32_t dim_mask, double* d_max_time, double* d_max_value, int32_t* d_max_segment,
-                    double* d_min_time, double* d_min_value, int32_t* d_min_segment, double* d_root_times,
-                    int32_t* d_root_count, minsnap_stream_t stream) {
+                    double* d_min_time, double* d_min_value, int32_t* d_min_segment, double* d_cand_times,
+                    double* d_cand_values, int32_t* d_root_count, minsnap_stream_t stream) {
   if (!extrema_args_ok(B, K, D, N, derivative, mode, &dim_mask)) return MINSNAP_ERR_ARG;
   if (B == 0) return MINSNAP_OK;
   if (!d_coeffs || !d_times) return MINSNAP_ERR_ARG;
@@ -426,7 +426,7 @@ int minsnap_extrema(long B, int K, int D, int N, const double* d_coeffs, const d
   a.d_coeffs = d_coeffs; a.d_times = d_times;
   a.d_max_time = d_max_time; a.d_max_value = d_max_value; a.d_max_segment = d_max_segment;
   a.d_min_time = d_min_time; a.d_min_value = d_min_value; a.d_min_segment = d_min_segment;
-  a.d_root_times = d_root_times; a.d_root_count = d_root_count;
+  a.d_cand_times = d_cand_times; a.d_cand_values = d_cand_values; a.d_root_count = d_root_count;
   a.max_roots = minsnap::extrema_max_roots(N, derivative, __builtin_popcount(dim_mask));
   CU(minsnap::launch_extrema(a, as_stream(stream)));
   return MINSNAP_OK;
@@ -651,13 +651,13 @@ int minsnap_cost_host(long B, int K, int D, int N, int derivative, const double*
 int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs, const double* h_times, int derivative,
                          int mode, uint32_t dim_mask, double* h_max_time, double* h_max_value,
                          int32_t* h_max_segment, double* h_min_time, double* h_min_value, int32_t* h_min_segment,
-                         double* h_root_times, int32_t* h_root_count) {
+                         double* h_cand_times, double* h_cand_values, int32_t* h_root_count) {
   if (!extrema_args_ok(B, K, D, N, derivative, mode, &dim_mask)) return MINSNAP_ERR_ARG;
   if (B == 0) return MINSNAP_OK;
   if (!h_coeffs || !h_times) return MINSNAP_ERR_ARG;
   const size_t nb = (size_t)B;
   const size_t max_roots = (size_t)minsnap::extrema_max_roots(N, derivative, __builtin_popcount(dim_mask));
-  const size_t root_bytes = sizeof(double) * nb * K * (max_roots ? max_roots : 1);
+  const size_t cand_bytes = sizeof(double) * nb * K * (max_roots + 2);
   {
     SmallCall sc(cudaStreamPerThread);
     const int i_coeffs = sc.in(h_coeffs, sizeof(double) * nb * K * D * N);
@@ -668,14 +668,16 @@ int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs, co
     const int o_nt = sc.out(h_min_time, sizeof(double) * nb);
     const int o_nv = sc.out(h_min_value, sizeof(double) * nb);
     const int o_ns = sc.out(h_min_segment, sizeof(int32_t) * nb);
-    const int o_rt = h_root_times ? sc.out(h_root_times, root_bytes) : -1;
+    const int o_ct = h_cand_times ? sc.out(h_cand_times, cand_bytes) : -1;
+    const int o_cv = h_cand_values ? sc.out(h_cand_values, cand_bytes) : -1;
     const int o_rc = h_root_count ? sc.out(h_root_count, sizeof(int32_t) * nb * K) : -1;
     if (sc.total_bytes() <= kSmallCallBytes) {
       CU(sc.upload());
       const int rc = minsnap_extrema(B, K, D, N, sc.dev<double>(i_coeffs), sc.dev<double>(i_times), derivative, mode,
                                      dim_mask, sc.dev<double>(o_xt), sc.dev<double>(o_xv), sc.dev<int32_t>(o_xs),
                                      sc.dev<double>(o_nt), sc.dev<double>(o_nv), sc.dev<int32_t>(o_ns),
-                                     o_rt >= 0 ? sc.dev<double>(o_rt) : nullptr,
+                                     o_ct >= 0 ? sc.dev<double>(o_ct) : nullptr,
+                                     o_cv >= 0 ? sc.dev<double>(o_cv) : nullptr,
                                      o_rc >= 0 ? sc.dev<int32_t>(o_rc) : nullptr, cudaStreamPerThread);
       if (rc != MINSNAP_OK) return rc;
       CU(sc.download());
@@ -685,7 +687,7 @@ int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs, co
   cudaStream_t st = cudaStreamPerThread;
   int rc = MINSNAP_OK;
   {
-    Scratch co, tm, xt, xv, xs, nt, nv, ns, rt, rcnt;
+    Scratch co, tm, xt, xv, xs, nt, nv, ns, ctm, cvl, rcnt;
     TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
     TRY(tm.alloc(sizeof(double) * nb * K, st));
     TRY(xt.alloc(sizeof(double) * nb, st));
@@ -694,13 +696,15 @@ int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs, co
     TRY(nt.alloc(sizeof(double) * nb, st));
     TRY(nv.alloc(sizeof(double) * nb, st));
     TRY(ns.alloc(sizeof(int32_t) * nb, st));
-    if (h_root_times) TRY(rt.alloc(root_bytes, st));
+    if (h_cand_times) TRY(ctm.alloc(cand_bytes, st));
+    if (h_cand_values) TRY(cvl.alloc(cand_bytes, st));
     if (h_root_count) TRY(rcnt.alloc(sizeof(int32_t) * nb * K, st));
     TRY(cudaMemcpyAsync(co.ptr, h_coeffs, sizeof(double) * nb * K * D * N, cudaMemcpyHostToDevice, st));
     TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
     rc = minsnap_extrema(B, K, D, N, co.as<double>(), tm.as<double>(), derivative, mode, dim_mask, xt.as<double>(),
                          xv.as<double>(), xs.as<int32_t>(), nt.as<double>(), nv.as<double>(), ns.as<int32_t>(),
-                         h_root_times ? rt.as<double>() : nullptr, h_root_count ? rcnt.as<int32_t>() : nullptr, st);
+                         h_cand_times ? ctm.as<double>() : nullptr, h_cand_values ? cvl.as<double>() : nullptr,
+                         h_root_count ? rcnt.as<int32_t>() : nullptr, st);
     if (rc != MINSNAP_OK) goto done;
     if (h_max_time) TRY(cudaMemcpyAsync(h_max_time, xt.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
     if (h_max_value) TRY(cudaMemcpyAsync(h_max_value, xv.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
@@ -710,7 +714,8 @@ int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs, co
       if (h_min_value) TRY(cudaMemcpyAsync(h_min_value, nv.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
       if (h_min_segment) TRY(cudaMemcpyAsync(h_min_segment, ns.ptr, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
     }
-    if (h_root_times) TRY(cudaMemcpyAsync(h_root_times, rt.ptr, root_bytes, cudaMemcpyDeviceToHost, st));
+    if (h_cand_times) TRY(cudaMemcpyAsync(h_cand_times, ctm.ptr, cand_bytes, cudaMemcpyDeviceToHost, st));
+    if (h_cand_values) TRY(cudaMemcpyAsync(h_cand_values, cvl.ptr, cand_bytes, cudaMemcpyDeviceToHost, st));
     if (h_root_count)
       TRY(cudaMemcpyAsync(h_root_count, rcnt.ptr, sizeof(int32_t) * nb * K, cudaMemcpyDeviceToHost, st));
   done:;

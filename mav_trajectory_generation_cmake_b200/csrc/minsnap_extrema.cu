@@ -73,22 +73,48 @@ __device__ __forceinline__ void poly_value_slope_bound(const double (&d)[DEG + 1
   e = err;
 }
 
-// One root of a monotone piece: f(lo) and f(hi) have opposite signs.  Newton from the midpoint,
-// bisection whenever the step leaves the bracket; stops when |f| is inside its own rounding error
-// (nothing more can be learnt from the sign of f), when the step no longer changes x, or when
-// the bracket has collapsed.
 template <int DEG>
-__device__ __forceinline__ double refine_bracket(const double (&d)[DEG + 1], double lo, double hi, bool lo_negative) {
-  double x = 0.5 * (lo + hi);
-  for (int it = 0; it < 128; ++it) {
-    double f, fp, e;
-    poly_value_slope_bound<DEG>(d, x, f, fp, e);
-    if (fabs(f) <= DBL_EPSILON * e) return x;
+__device__ __forceinline__ void poly_value_slope(const double (&d)[DEG + 1], double t, double& f, double& fp) {
+  double a = d[DEG], b = 0.0;
+#pragma unroll
+  for (int j = DEG - 1; j >= 0; --j) {
+    b = fma(b, t, a);
+    a = fma(a, t, d[j]);
+  }
+  f = a;
+  fp = b;
+}
+
+// One root of a monotone piece: f(lo) and f(hi) have opposite signs.  Starts from the secant
+// point of the bracket, then Newton, with bisection whenever the step leaves the bracket.  Stops
+// when |f| is inside the rounding error of its own evaluation (bound taken at the starting point;
+// nothing more can be learnt from the sign of f), when the step is below rel_tol, or when the
+// bracket has collapsed.  Roots of the derivative levels only separate monotone pieces of the next
+// level, so they are refined to 1e-10 only; the roots of g itself to full precision.
+// (Measured alternative: collecting the brackets of a level first and refining the r-th bracket of
+// every lane together was slower, 3.9 ms against 2.5 ms, although more lanes are active per step.)
+template <int DEG>
+__device__ __forceinline__ double refine_bracket(const double (&d)[DEG + 1], double lo, double hi, double f_lo,
+                                                 double f_hi, double rel_tol) {
+  const bool lo_negative = f_lo < 0.0;
+  double x = lo - f_lo * ((hi - lo) / (f_hi - f_lo));
+  if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
+  double f_noise = 0.0;
+  for (int it = 0; it < 64; ++it) {
+    double f, fp;
+    if (it == 0) {
+      double e;
+      poly_value_slope_bound<DEG>(d, x, f, fp, e);
+      f_noise = DBL_EPSILON * e;
+    } else {
+      poly_value_slope<DEG>(d, x, f, fp);
+    }
+    if (fabs(f) <= f_noise) return x;
     if ((f < 0.0) == lo_negative) lo = x; else hi = x;
     double next = fp != 0.0 ? x - f / fp : lo - 1.0;
     if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);
     if (next == lo || next == hi) return next;
-    if (fabs(next - x) <= 2.0 * DBL_EPSILON * fabs(next)) return next;
+    if (fabs(next - x) <= rel_tol * fabs(next)) return next;
     x = next;
   }
   return x;
@@ -116,7 +142,7 @@ __device__ __noinline__ int root_level(const double (&g)[LEN], double t0, double
     if (f_right == 0.0) {
       cur[n_cur++] = right;
     } else if (f_left != 0.0 && (f_left < 0.0) != (f_right < 0.0)) {
-      cur[n_cur++] = refine_bracket<DEG>(d, left, right, f_left < 0.0);
+      cur[n_cur++] = refine_bracket<DEG>(d, left, right, f_left, f_right, M == 0 ? 2.0 * DBL_EPSILON : 1e-10);
     }
     left = right;
     f_left = f_right;
@@ -162,7 +188,8 @@ struct ExtremaParams {
   const double* coeffs;
   const double* times;
   SegmentExtremum* per_segment;  // [B][K]
-  double* root_times;            // optional [B][K][max_roots]
+  double* cand_times;            // optional [B][K][max_roots + 2]: start, end, roots
+  double* cand_values;           // optional, same shape: the magnitude at each candidate
   int32_t* root_count;           // optional [B][K]
   int max_roots;
 };
@@ -250,36 +277,41 @@ __global__ void __launch_bounds__(128) segment_extrema_kernel(ExtremaParams p) {
   const double* roots = buf_a;
   if (last >= 1 && T >= 0.0) roots = real_roots<LEN>(g, last, 0.0, T, buf_a, buf_b, n_roots);
 
+  // Candidate list in the order of Segment::computeMinMaxMagnitudeCandidates (src/polynomial.cpp:39-40,
+  // src/segment.cpp:133-156): start, end, then the roots.
+  const bool list = p.cand_times != nullptr || p.cand_values != nullptr;
+  const long stride = p.max_roots + 2;
+  double* ct = p.cand_times ? p.cand_times + idx * stride : nullptr;
+  double* cv = p.cand_values ? p.cand_values + idx * stride : nullptr;
   if (p.root_count) p.root_count[idx] = n_roots;
-  if (p.root_times)
-    for (int i = 0; i < n_roots && i < p.max_roots; ++i) p.root_times[idx * p.max_roots + i] = roots[i];
 
   SegmentExtremum e;
   const bool last_segment = (idx % p.K) == p.K - 1;
+  const double v_start = magnitude_at(seg, D, N, p.dim_mask, k, 0.0);
+  const bool need_end = p.mode != 0 || last_segment || list;
+  const double v_end = need_end ? magnitude_at(seg, D, N, p.dim_mask, k, T) : 0.0;
+  if (ct) { ct[0] = 0.0; ct[1] = T; }
+  if (cv) { cv[0] = v_start; cv[1] = v_end; }
+  e.max_t = e.min_t = 0.0;
+  e.max_v = e.min_v = v_start;
+  if (p.mode != 0) {
+    // mode 1: start, end, roots (strict comparisons: the first extremal candidate wins)
+    if (e.max_v < v_end) { e.max_v = v_end; e.max_t = T; }
+    if (v_end < e.min_v) { e.min_v = v_end; e.min_t = T; }
+  }
+  for (int i = 0; i < n_roots; ++i) {
+    const double t = roots[i];
+    const double v = magnitude_at(seg, D, N, p.dim_mask, k, t);
+    if (ct) ct[2 + i] = t;
+    if (cv) cv[2 + i] = v;
+    if (e.max_v < v) { e.max_v = v; e.max_t = t; }
+    if (v < e.min_v) { e.min_v = v; e.min_t = t; }
+  }
   if (p.mode == 0) {
-    // candidates: 0, roots, (last segment only) T; strictly larger replaces (LIN.i:486-499)
-    e.max_t = 0.0;
-    e.max_v = magnitude_at(seg, D, N, p.dim_mask, k, 0.0);
-    for (int i = 0; i < n_roots; ++i) {
-      const double v = magnitude_at(seg, D, N, p.dim_mask, k, roots[i]);
-      if (e.max_v < v) { e.max_v = v; e.max_t = roots[i]; }
-    }
-    if (last_segment) {
-      const double v = magnitude_at(seg, D, N, p.dim_mask, k, T);
-      if (e.max_v < v) { e.max_v = v; e.max_t = T; }
-    }
+    // mode 0: 0, roots, and the end of the last segment only (LIN.i:486-499); no minimum
+    if (last_segment && e.max_v < v_end) { e.max_v = v_end; e.max_t = T; }
     e.min_t = 0.0;
     e.min_v = 0.0;
-  } else {
-    // candidates: start, end, roots (src/polynomial.cpp:39-40, src/segment.cpp:171-179)
-    e.max_t = e.min_t = 0.0;
-    e.max_v = e.min_v = magnitude_at(seg, D, N, p.dim_mask, k, 0.0);
-    for (int i = -1; i < n_roots; ++i) {
-      const double t = i < 0 ? T : roots[i];
-      const double v = magnitude_at(seg, D, N, p.dim_mask, k, t);
-      if (e.max_v < v) { e.max_v = v; e.max_t = t; }
-      if (v < e.min_v) { e.min_v = v; e.min_t = t; }
-    }
   }
   p.per_segment[idx] = e;
 }
@@ -342,7 +374,8 @@ cudaError_t launch_extrema(const ExtremaArgs& a, cudaStream_t stream) {
   p.dim_mask = a.dim_mask;
   p.coeffs = a.d_coeffs; p.times = a.d_times;
   p.per_segment = static_cast<SegmentExtremum*>(scratch);
-  p.root_times = a.d_root_times; p.root_count = a.d_root_count; p.max_roots = a.max_roots;
+  p.cand_times = a.d_cand_times; p.cand_values = a.d_cand_values; p.root_count = a.d_root_count;
+  p.max_roots = a.max_roots;
   e = len <= 4    ? launch_segments<4>(p, stream)
       : len <= 6  ? launch_segments<6>(p, stream)
       : len <= 8  ? launch_segments<8>(p, stream)

@@ -100,7 +100,8 @@ struct ExtremaArgs {
   double* d_min_time;      // mode 1 only
   double* d_min_value;
   int32_t* d_min_segment;
-  double* d_root_times;    // optional [B][K][max_roots]
+  double* d_cand_times;    // optional [B][K][max_roots + 2]: start, end, roots (ascending)
+  double* d_cand_values;   // optional, same shape
   int32_t* d_root_count;   // optional [B][K]
   int max_roots;
 };

@@ -336,6 +336,109 @@ static void testRangeAndBatch() {
   }
 }
 
+// T:396-416 checkExtrema: every analytic candidate has a sampled one within tol
+static bool checkExtrema(const std::vector<double>& testee, const std::vector<double>& reference, double tol = 0.01) {
+  for (double t : testee) {
+    bool found_match = false;
+    for (double r : reference)
+      if (std::fabs(t - r) < tol) {
+        found_match = true;
+        break;
+      }
+    if (!found_match) {
+      std::printf("  no sampled extremum near t = %.6f\n", t);
+      return false;
+    }
+  }
+  return true;
+}
+
+// T:418-507 (1-D) and T:509-612 (3-D): segment extrema of magnitude, analytic against sampling
+static void testExtremaOfMagnitude(int D, int n_segments, size_t seed) {
+  Vertex::Vector vertices;
+  if (D == 1) {
+    vertices = createRandomVertices1D(max_derivative, n_segments, -10, 10, seed);
+  } else {
+    Eigen::VectorXd pos_min(3), pos_max(3);
+    pos_min << -10.0, -9.0, -8.0;
+    pos_max << 8.0, 9.0, 10.0;
+    vertices = createRandomVertices(max_derivative, n_segments, pos_min, pos_max, seed);
+  }
+  std::vector<double> segment_times = estimateSegmentTimes(vertices, 3.0, 5.0);
+  PolynomialOptimization<N> opt(D);
+  opt.setupFromVertices(vertices, segment_times, derivative_to_optimize);
+  opt.solveLinear();
+  Segment::Vector segments;
+  opt.getSegments(&segments);
+
+  std::vector<int> dimensions;
+  for (int d = 0; d < D; ++d) dimensions.push_back(d);
+  int segment_idx = 0;
+  for (const Segment& s : segments) {
+    if (segment_idx % 5 == 0) {   // every fifth segment: the sampled comparison costs 2 launches each
+      std::vector<double> res, res_template_free, res_sampling;
+      opt.computeSegmentMaximumMagnitudeCandidates<1>(s, 0, s.getTime(), &res);
+      s.computeMinMaxMagnitudeCandidateTimes(1, 0.0, s.getTime(), dimensions, &res_template_free);
+      opt.computeSegmentMaximumMagnitudeCandidatesBySampling<1>(s, 0, s.getTime(), 0.001, &res_sampling);
+      // the rest ends carry a root of multiplicity 7 that floating point splits into a cluster
+      std::vector<double> simple;
+      for (double t : res) {
+        const bool rest_end = (segment_idx == 0 && t < 0.02 * s.getTime()) ||
+                              (segment_idx == n_segments - 1 && t > 0.98 * s.getTime());
+        if (!rest_end) simple.push_back(t);
+      }
+      EXPECT_TRUE(checkExtrema(simple, res_sampling, 0.01));
+      EXPECT_EQ(res.size(), res_template_free.size() - 2);
+      for (size_t i = 0; i < res.size() && i + 2 < res_template_free.size(); i++)
+        EXPECT_EQ(res[i], res_template_free[i + 2]);
+    }
+    ++segment_idx;
+  }
+
+  // the exact candidate polynomial for the comparison with sampling (the reference's coefficient
+  // threshold loses extrema on the few segments longer than ~12 s)
+  gpu::keepSmallCoefficients(true);
+  const double v_max_ref = maximumMagnitude(segments, derivative_order::VELOCITY);
+  const double a_max_ref = maximumMagnitude(segments, derivative_order::ACCELERATION);
+  std::vector<Extremum> candidates;
+  const Extremum v_max = opt.computeMaximumOfMagnitude<derivative_order::VELOCITY>(&candidates);
+  const Extremum a_max = opt.computeMaximumOfMagnitude<derivative_order::ACCELERATION>(nullptr);
+  EXPECT_LT(std::fabs(v_max_ref - v_max.value), 0.01);
+  EXPECT_LT(std::fabs(a_max_ref - a_max.value), 0.01);
+  // the candidate list holds the reported maximum, and nothing larger
+  bool found = false;
+  for (const Extremum& c : candidates) {
+    EXPECT_TRUE(c.value <= v_max.value);
+    found = found || (c.value == v_max.value && c.time == v_max.time && c.segment_idx == v_max.segment_idx);
+  }
+  EXPECT_TRUE(found);
+  EXPECT_TRUE(candidates.size() >= static_cast<size_t>(n_segments + 1));
+  // Trajectory::computeMinMaxMagnitude agrees with the optimisation's maximum
+  Trajectory trajectory;
+  opt.getTrajectory(&trajectory);
+  Extremum t_min, t_max;
+  EXPECT_TRUE(trajectory.computeMinMaxMagnitude(derivative_order::VELOCITY, dimensions, &t_min, &t_max));
+  EXPECT_LT(std::fabs(t_max.value - v_max.value), 1e-9);
+  EXPECT_LT(t_min.value, 1e-9);   // rest to rest
+  // and with the per-segment route
+  Extremum s_min, s_max;
+  std::vector<Extremum> seg_candidates;
+  const Segment& seg = segments[static_cast<size_t>(t_max.segment_idx)];
+  EXPECT_TRUE(seg.computeMinMaxMagnitudeCandidates(derivative_order::VELOCITY, 0.0, seg.getTime(), dimensions,
+                                                   &seg_candidates));
+  EXPECT_TRUE(seg.selectMinMaxMagnitudeFromCandidates(0.0, seg.getTime(), derivative_order::VELOCITY, dimensions,
+                                                      seg_candidates, &s_min, &s_max));
+  EXPECT_LT(std::fabs(s_max.value - t_max.value), 1e-9);
+  gpu::keepSmallCoefficients(false);
+  // reference-compatible mode: never above the exact maximum
+  const Extremum v_compat = opt.computeMaximumOfMagnitude<derivative_order::VELOCITY>(nullptr);
+  EXPECT_TRUE(v_compat.value <= v_max.value * (1 + 1e-12));
+  // bad arguments keep the reference's conventions (src/segment.cpp:89-102)
+  std::vector<double> none;
+  EXPECT_TRUE(!segments[0].computeMinMaxMagnitudeCandidateTimes(1, 0.0, 1.0, std::vector<int>(), &none));
+  EXPECT_TRUE(!segments[0].computeMinMaxMagnitudeCandidateTimes(1, 0.0, 1.0, std::vector<int>{0, D}, &none));
+}
+
 int main() {
   struct Case {
     const char* name;
@@ -354,6 +457,8 @@ int main() {
       {"2_vertices_rand", testTwoVerticesRand},
       {"ConstraintPacking", testConstraintPacking},
       {"EvaluateRange_and_Batch", testRangeAndBatch},
+      {"PathOptimization_1D_segment_extrema_of_magnitude", [] { testExtremaOfMagnitude(1, 100, 1234); }},
+      {"PathOptimization3D_segment_extrema_of_magnitude", [] { testExtremaOfMagnitude(3, 100, 978); }},
   };
   for (const Case& c : cases) {
     const int before = g_failures;

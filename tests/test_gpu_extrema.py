@@ -51,6 +51,13 @@ def check_against_oracle(oracle, coeffs_h, times_h, got, k, mode, dims=None, kee
                 mine = got["root_times"][b, s, : got["root_count"][b, s]]
                 theirs = want["candidates"][s]
                 assert np.all(np.diff(mine) >= 0)
+                # candidate list: start, end, roots -- each with the magnitude there
+                n_c = 2 + got["root_count"][b, s]
+                ct, cv = got["cand_times"][b, s, :n_c], got["cand_values"][b, s, :n_c]
+                assert ct[0] == 0.0 and ct[1] == T
+                for t_c, v_c in zip(ct, cv):
+                    re = oracle.segment_magnitude(coeffs_h[b, s], k, t_c, dims=dims)
+                    assert abs(re - v_c) <= 1e-9 * max(abs(re), 1.0)
                 inner = lambda r: np.array([t for t in r if 0.03 * T < t < 0.97 * T])  # noqa: E731
                 a, c = inner(theirs), inner(mine)
                 if len(a) == len(c):
