@@ -299,6 +299,16 @@ def run_gpu_arm(args):
         sample_ms = s0.elapsed_time(s1) / reps
         samples_per_s = B * M / (sample_ms * 1e-3)
         del samples
+        # extrema of |velocity| over every trajectory (computeMaximumOfMagnitude)
+        for _ in range(2):
+            ms.extrema(coeffs_d[0], times_d[0], 1)
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for _ in range(reps):
+            ms.extrema(coeffs_d[0], times_d[0], 1)
+        x1.record()
+        torch.cuda.synchronize()
+        extrema_ms = x0.elapsed_time(x1) / reps
 
         cores = os.cpu_count() or 1
         cpu_value, cpu_sample, cpu_1t = cpu_solves_per_s(pos_h, times_pin.numpy(), cores, budget_s=15.0)
@@ -325,6 +335,9 @@ def run_gpu_arm(args):
             "extra": {"samples_per_s": samples_per_s, "sample_ms": sample_ms,
                       "sample_hbm_frac": samples_per_s * 120.0 / 1e9 / hbm_peak,
                       "sample_shape": "%d trajectories x %d instants x (pos..snap) x 3" % (B, M),
+                      "extrema_ms": extrema_ms, "extrema_trajectories_per_s": B / (extrema_ms * 1e-3),
+                      "extrema_shape": "max |velocity| of %d trajectories x %d segments "
+                                       "(computeMaximumOfMagnitude)" % (B, K_SEG),
                       "nccl_gather_ms": gather_ms},
         }
         print(json.dumps(line), flush=True)

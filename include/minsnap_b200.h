@@ -212,6 +212,28 @@ MINSNAP_API int minsnap_extrema(long B, int K, int D, int N, const double* d_coe
                                 double* d_cand_times, double* d_cand_values, int32_t* d_root_count,
                                 minsnap_stream_t stream);
 
+/* ---- the time-only objective and its numeric gradient ------------------------
+ * minsnap_time_objective (ref objectiveFunctionTime, NL.i:765-832, without the collision and
+ * soft-constraint terms): for every trajectory b and candidate time allocation s
+ *   objective[b][s] = computeCost(solveLinear(times[b][s])) + time_penalty * (sum_k times[b][s][k])^2.
+ * Standard mask (as minsnap_cost_sweep, which it runs); d_cost [B][S] optional.
+ * minsnap_time_gradient (ref getCostAndGradientTime, NL.i:2155-2243): central differences of
+ * J_d = d^T R d (= 2 computeCost; ref getCostAndGradientDerivative, NL.i:1452-1521) in each
+ * segment time, the end-point derivatives d of the solved trajectory held fixed as in the
+ * reference; a time <= 0.1 is moved to 0.1 instead of -/+ increment:
+ *   gradient[b][n] = w_d (J_d(T_n+) - J_d(T_n-)) / (2 increment) + w_t.
+ * Input: the solved coefficients.  d_segment_cost [B][K] optional: the per-segment terms of J_d
+ * at the given times (their sum over n is J_d). */
+MINSNAP_API int minsnap_time_objective(long B, int S, int K, int D, int N, int derivative,
+                                       const double* d_positions, const double* d_end_derivatives,
+                                       const double* d_times, double time_penalty,
+                                       double* d_objective, double* d_cost, int32_t* d_status,
+                                       minsnap_stream_t stream);
+MINSNAP_API int minsnap_time_gradient(long B, int K, int D, int N, int derivative,
+                                      const double* d_coeffs, const double* d_times,
+                                      double increment, double w_d, double w_t, double* d_gradient,
+                                      double* d_segment_cost, minsnap_stream_t stream);
+
 /* ---- host-buffer entry points (synchronous; copies inside) -------------------------------
  * The calls a host program makes when its data lives in host memory.  Work is cut into
  * chunks that are copied and solved on alternating streams so that PCIe and the SMs overlap.

@@ -234,6 +234,66 @@ def cost_sweep(positions, times, end_derivatives=None, N=10, derivative=SNAP, wa
     return (out, status) if want_status else out
 
 
+def time_objective(positions, times, time_penalty, end_derivatives=None, N=10, derivative=SNAP, want_cost=False):
+    """positions [B][K+1][D], times [B][S][K] -> objective [B][S] = computeCost + time_penalty * total_time^2
+    (ref objectiveFunctionTime, NL.i:765-832, derivative and time terms)."""
+    torch = _torch()
+    B, K1, D = positions.shape
+    S = times.shape[1]
+    out = torch.empty((B, S), dtype=torch.float64, device=positions.device)
+    cost_t = torch.empty((B, S), dtype=torch.float64, device=positions.device) if want_cost else None
+    capi.check(_lib().minsnap_time_objective(B, S, K1 - 1, D, N, derivative, _dptr(positions, torch.float64),
+                                             _dptr(end_derivatives), _dptr(times, torch.float64), float(time_penalty),
+                                             _dptr(out), _dptr(cost_t), None, _stream()), "minsnap_time_objective")
+    return (out, cost_t) if want_cost else out
+
+
+def time_gradient(coeffs, times, increment=0.1, w_d=0.1, w_t=1.0, derivative=SNAP, want_segment_cost=False):
+    """Numeric gradient of w_d J_d + w_t total_time in the segment times (ref getCostAndGradientTime,
+    NL.i:2155-2243; defaults are the reference's increment_time and cost weights).  coeffs [B][K][D][N]
+    are the solved coefficients -> gradient [B][K] (and the per-segment terms of J_d = 2 computeCost)."""
+    torch = _torch()
+    B, K, D, N = coeffs.shape
+    grad = torch.empty((B, K), dtype=torch.float64, device=coeffs.device)
+    seg = torch.empty((B, K), dtype=torch.float64, device=coeffs.device) if want_segment_cost else None
+    capi.check(_lib().minsnap_time_gradient(B, K, D, N, derivative, _dptr(coeffs, torch.float64),
+                                            _dptr(times, torch.float64), float(increment), float(w_d), float(w_t),
+                                            _dptr(grad), _dptr(seg), _stream()), "minsnap_time_gradient")
+    return (grad, seg) if want_segment_cost else grad
+
+
+def optimize_segment_times(positions, times, iterations=20, time_penalty=500.0, n_steps=16, max_relative_step=0.5,
+                           min_time=0.1, end_derivatives=None):
+    """Additive batched driver for the time-only problem: every trajectory of the batch
+    descends objective = computeCost + time_penalty * total_time^2 along its own numeric gradient
+    (minsnap_time_gradient), with the line search done in parallel -- n_steps candidate step lengths per
+    trajectory are evaluated by one minsnap_time_objective launch and the best one (or none) is kept.
+    Everything stays on the device; the reference runs one NLopt instance per trajectory on the host.
+    Returns (times, objective history [iterations + 1][B])."""
+    torch = _torch()
+    B, K1, D = positions.shape
+    K = K1 - 1
+    times = times.clone()
+    history = [time_objective(positions, times[:, None, :].contiguous(), time_penalty, end_derivatives)[:, 0]]
+    # geometric ladder of relative step lengths: the longest moves the largest component by max_relative_step
+    ladder = max_relative_step * 0.5 ** torch.arange(n_steps, dtype=torch.float64, device=positions.device)
+    for _ in range(iterations):
+        coeffs = solve_standard(positions, times, end_derivatives=end_derivatives, want_status=False)["coeffs"]
+        # objective gradient: d cost / dT = 0.5 dJ_d/dT (w_d = 0.5, w_t = 0) + d/dT penalty * total^2
+        g = time_gradient(coeffs, times, increment=1e-3, w_d=0.5, w_t=0.0)
+        g = g + 2.0 * time_penalty * times.sum(1, keepdim=True)
+        scale = (times / g.abs().clamp_min(1e-300)).min(1, keepdim=True).values   # step that would zero a time
+        cand = times[:, None, :] - (ladder[None, :, None] * scale[:, :, None]) * g[:, None, :]
+        cand = cand.clamp_min(min_time).contiguous()
+        obj = time_objective(positions, cand, time_penalty, end_derivatives)
+        best, arg = obj.min(1)
+        improved = best < history[-1]
+        chosen = cand[torch.arange(B, device=cand.device), arg]
+        times = torch.where(improved[:, None], chosen, times)
+        history.append(torch.where(improved, best, history[-1]))
+    return times, torch.stack(history)
+
+
 EXTREMA_OPTIMIZATION = 0   # PolynomialOptimization::computeMaximumOfMagnitude (ref LIN.i:470-503)
 EXTREMA_TRAJECTORY = 1     # Trajectory::computeMinMaxMagnitude (ref src/trajectory.cpp:181-217)
 EXTREMA_KEEP_SMALL_COEFFICIENTS = 16   # OR into mode: do not truncate coefficients below 2.2e-16

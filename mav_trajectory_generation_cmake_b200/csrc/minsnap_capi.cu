@@ -432,6 +432,33 @@ int minsnap_extrema(long B, int K, int D, int N, const double* d_coeffs, const d
   return MINSNAP_OK;
 }
 
+// time-only objective (ref NL.i:765-832) and numeric time gradient (ref NL.i:2155-2243)
+int minsnap_time_objective(long B, int S, int K, int D, int N, int derivative, const double* d_positions,
+                           const double* d_end_derivatives, const double* d_times, double time_penalty,
+                           double* d_objective, double* d_cost, int32_t* d_status, minsnap_stream_t stream) {
+  if (!shape_ok(B, K, D, N, derivative) || S < 1) return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  if (!d_positions || !d_times || !d_objective) return MINSNAP_ERR_ARG;
+  // the cost lands in d_cost when given, else in d_objective, and is completed in place
+  double* cost = d_cost ? d_cost : d_objective;
+  const int rc = minsnap_cost_sweep(B, S, K, D, N, derivative, d_positions, d_end_derivatives, d_times, cost, d_status,
+                                    stream);
+  if (rc != MINSNAP_OK) return rc;
+  CU(minsnap::launch_add_time_penalty(B * S, K, d_times, cost, time_penalty, d_objective, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
+int minsnap_time_gradient(long B, int K, int D, int N, int derivative, const double* d_coeffs, const double* d_times,
+                          double increment, double w_d, double w_t, double* d_gradient, double* d_segment_cost,
+                          minsnap_stream_t stream) {
+  if (!shape_ok(B, K, D, N, derivative) || !(increment > 0.0)) return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  if (!d_coeffs || !d_times || (!d_gradient && !d_segment_cost)) return MINSNAP_ERR_ARG;
+  CU(minsnap::launch_time_gradient(B, K, D, N, derivative, d_coeffs, d_times, increment, w_d, w_t, d_gradient,
+                                   d_segment_cost, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // Host-buffer entry points
 // ---------------------------------------------------------------------------------------

@@ -487,4 +487,96 @@ cudaError_t launch_cost(long B, int K, int D, int N, int derivative, const doubl
   return cudaGetLastError();
 }
 
+// =========================================================================================
+// numeric time gradient of the derivative cost (ref: getCostAndGradientTime,
+// NL.i:2155-2243, with J_d = d^T R d from getCostAndGradientDerivative, NL.i:1452-1521).
+// The reference moves ONE segment time by -/+ increment (a time <= 0.1 is set to 0.1 instead),
+// rebuilds R and evaluates d^T R d with the end-point derivatives d of the last solve held
+// fixed; only the moved segment's term q(T') = sum_dim d_seg^T H(T') d_seg changes, so
+//   gradient[n] = w_d (q_n(T+) - q_n(T-)) / (2 increment) + w_t.
+// One thread per (trajectory, segment): d_seg from the coefficients (derivatives at 0 and T),
+// H(T') = H1 .* T'^(k_r + k_s + 1 - 2 delta) from the exact unit-time table.
+// =========================================================================================
+template <int N>
+__global__ void __launch_bounds__(128) time_gradient_kernel(long B, int K, int D, int delta,
+                                                            const double* __restrict__ coeffs,
+                                                            const double* __restrict__ times, double increment,
+                                                            double w_d, double w_t, double* __restrict__ gradient,
+                                                            double* __restrict__ segment_cost) {
+  constexpr int h = N / 2;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * K) return;
+  const double T = times[idx];
+  const double T_minus = T <= 0.1 ? 0.1 : T - increment;
+  const double T_plus = T <= 0.1 ? 0.1 : T + increment;
+  // T'^(m + 1 - 2 delta) for m = k_r + k_s = 0 .. 2h-2
+  double pw0[2 * h - 1], pwm[2 * h - 1], pwp[2 * h - 1];
+#pragma unroll
+  for (int m = 0; m < 2 * h - 1; ++m) {
+    pw0[m] = int_power(T, m + 1 - 2 * delta);
+    pwm[m] = int_power(T_minus, m + 1 - 2 * delta);
+    pwp[m] = int_power(T_plus, m + 1 - 2 * delta);
+  }
+  const double* H1 = UnitTables<N>::h1(delta);
+  double q0 = 0.0, qm = 0.0, qp = 0.0;
+  for (int dim = 0; dim < D; ++dim) {
+    const double* c = coeffs + (idx * D + dim) * N;
+    double dv[N];
+#pragma unroll
+    for (int k = 0; k < h; ++k) {
+      dv[k] = falling_factorial(k, k) * c[k];
+      double r = falling_factorial(k, N - 1) * c[N - 1];
+#pragma unroll
+      for (int j = N - 2; j >= 0; --j)
+        if (j >= k) r = fma(r, T, falling_factorial(k, j) * c[j]);
+      dv[h + k] = r;
+    }
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+#pragma unroll
+      for (int s = 0; s < N; ++s) {
+        const int m = (r % h) + (s % h);
+        const double term = dv[r] * dv[s] * H1[r * N + s];
+        q0 = fma(term, pw0[m], q0);
+        qm = fma(term, pwm[m], qm);
+        qp = fma(term, pwp[m], qp);
+      }
+    }
+  }
+  if (gradient) gradient[idx] = w_d * ((qp - qm) / (2.0 * increment)) + w_t;
+  if (segment_cost) segment_cost[idx] = q0;
+}
+
+cudaError_t launch_time_gradient(long B, int K, int D, int N, int derivative, const double* d_coeffs,
+                                 const double* d_times, double increment, double w_d, double w_t, double* d_gradient,
+                                 double* d_segment_cost, cudaStream_t stream) {
+  if (B == 0) return cudaSuccess;
+  const long n = B * K;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  MINSNAP_DISPATCH_N(N, (time_gradient_kernel<kN><<<grid, 128, 0, stream>>>(B, K, D, derivative, d_coeffs, d_times,
+                                                                             increment, w_d, w_t, d_gradient,
+                                                                             d_segment_cost)));
+  return cudaGetLastError();
+}
+
+// objective[b][s] = cost[b][s] + time_penalty (sum_k times[b][s][k])^2  (ref objectiveFunctionTime,
+// NL.i:778-784: cost_trajectory + total_time^2 * time_penalty)
+__global__ void __launch_bounds__(256) add_time_penalty_kernel(long n, int K, const double* __restrict__ times,
+                                                               const double* __restrict__ cost, double time_penalty,
+                                                               double* __restrict__ objective) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double total = 0.0;
+  for (int k = 0; k < K; ++k) total += times[i * K + k];   // ref computeTotalTrajectoryTime: left to right
+  objective[i] = cost[i] + total * total * time_penalty;
+}
+
+cudaError_t launch_add_time_penalty(long n, int K, const double* d_times, const double* d_cost, double time_penalty,
+                                    double* d_objective, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  add_time_penalty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, K, d_times, d_cost, time_penalty,
+                                                                         d_objective);
+  return cudaGetLastError();
+}
+
 }  // namespace minsnap

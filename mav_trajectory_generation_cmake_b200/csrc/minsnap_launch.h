@@ -39,6 +39,13 @@ cudaError_t launch_coeffs_from_constraints(const GeneralSolveArgs& a, cudaStream
 cudaError_t launch_cost(long B, int K, int D, int N, int derivative, const double* d_coeffs,
                         const double* d_times, double* d_cost, cudaStream_t stream);
 
+// SURVEY 8(f)2 (ref getCostAndGradientTime NL.i:2155-2243, objectiveFunctionTime NL.i:765-832)
+cudaError_t launch_time_gradient(long B, int K, int D, int N, int derivative, const double* d_coeffs,
+                                 const double* d_times, double increment, double w_d, double w_t, double* d_gradient,
+                                 double* d_segment_cost, cudaStream_t stream);
+cudaError_t launch_add_time_penalty(long n, int K, const double* d_times, const double* d_cost, double time_penalty,
+                                    double* d_objective, cudaStream_t stream);
+
 // ---- minsnap_standard.cu ---------------------------------------------------------------
 struct StandardSolveArgs {
   long B;
