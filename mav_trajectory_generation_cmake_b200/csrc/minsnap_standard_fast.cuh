@@ -50,6 +50,14 @@ constexpr int kMaxK = 24;
 #define H1T(r, s) (minsnap_tables::kH1_N10_d4[(r) * 10 + (s)])
 #define A1T(i, r) (minsnap_tables::kA1inv_N10[(i) * 10 + (r)])
 // coefficient store policy (measurement knob): 0 streaming (evict-first), 1 plain, 2 .cg, 3 .wt
+// 256-bit streaming store (PTX 8.8, sm_100+: STG.E.EF.ENL2.256); ptr must be 32-byte aligned.
+__device__ __forceinline__ void store_cs_v4(double* ptr, double a, double b, double c, double d) {
+#if defined(MINSNAP_STORE_POLICY) && MINSNAP_STORE_POLICY == 9
+  if (a == 1.2345678e300)
+#endif
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 #ifndef MINSNAP_STORE_POLICY
 #define MINSNAP_STORE_POLICY 0
 #endif
@@ -59,6 +67,9 @@ constexpr int kMaxK = 24;
 #define MINSNAP_STORE2(ptr, val) __stcg(ptr, val)
 #elif MINSNAP_STORE_POLICY == 3
 #define MINSNAP_STORE2(ptr, val) __stwt(ptr, val)
+#elif MINSNAP_STORE_POLICY == 9
+// measurement only: the arithmetic stays, the store (practically) never executes
+#define MINSNAP_STORE2(ptr, val) do { if ((val).x == 1.2345678e300) __stcs(ptr, val); } while (0)
 #else
 #define MINSNAP_STORE2(ptr, val) __stcs(ptr, val)
 #endif
@@ -785,11 +796,28 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
           // the segment's D polynomials are 80 D contiguous, 16-byte aligned bytes of HBM
           double* dst = p.coeffs + (prob * K + seg) * (D * kN);
           if (p.aligned16) {
+            // 32-byte stores (st.global.v4.f64, new with sm_100) on 32-byte boundaries, one 16-byte
+            // store where the block starts or ends on a half sector: 8 store instructions per
+            // 240-byte block instead of 15, and L2 receives whole sectors.  Measured: the per-lane
+            // 16-byte stores (every lane in its own 128-byte line, half a sector each) were the
+            // kernel's bottleneck -- 72 us with them, 41 us with the stores compiled out.
+            constexpr int n = D * kN;
+#define MINSNAP_CF(e) cf[(e) / kN][(e) % kN]
+            if ((reinterpret_cast<uintptr_t>(dst) & 16) == 0) {
 #pragma unroll
-            for (int d = 0; d < D; ++d)
+              for (int e = 0; e + 4 <= n; e += 4)
+                store_cs_v4(dst + e, MINSNAP_CF(e), MINSNAP_CF(e + 1), MINSNAP_CF(e + 2), MINSNAP_CF(e + 3));
+              if (n % 4 == 2)
+                MINSNAP_STORE2(reinterpret_cast<double2*>(dst + n - 2), make_double2(MINSNAP_CF(n - 2), MINSNAP_CF(n - 1)));
+            } else {
+              MINSNAP_STORE2(reinterpret_cast<double2*>(dst), make_double2(MINSNAP_CF(0), MINSNAP_CF(1)));
 #pragma unroll
-              for (int i = 0; i < kN; i += 2)
-                MINSNAP_STORE2(reinterpret_cast<double2*>(dst + d * kN + i), make_double2(cf[d][i], cf[d][i + 1]));
+              for (int e = 2; e + 4 <= n; e += 4)
+                store_cs_v4(dst + e, MINSNAP_CF(e), MINSNAP_CF(e + 1), MINSNAP_CF(e + 2), MINSNAP_CF(e + 3));
+              if ((n - 2) % 4 == 2)
+                MINSNAP_STORE2(reinterpret_cast<double2*>(dst + n - 2), make_double2(MINSNAP_CF(n - 2), MINSNAP_CF(n - 1)));
+            }
+#undef MINSNAP_CF
           } else {
 #pragma unroll
             for (int d = 0; d < D; ++d)
@@ -867,17 +895,18 @@ inline cudaError_t launch_mode(FastParams p, cudaStream_t stream) {
   }
   if (per_warp * warps > kMaxDynamicSmem) return cudaErrorInvalidConfiguration;
   size_t smem = per_warp * warps;
-  // Resident warps per SM.  Measured on B200 (65,536 x K=10): the cost-only kernel keeps scaling up to
-  // the register limit of 8 warps, the coefficient-writing kernel is fastest at 6-7 (its per-lane
-  // 16-byte stores and the shrunken L1 make 8 slower), so that one is padded down to 7.
-  // MINSNAP_TUNE_MAX_WARPS overrides for measurements.
-  int cap = kCoeffs ? 7 : 8;
+  // Resident warps per SM.  Measured on B200 (65,536 x K=10) with the 32-byte coefficient stores:
+  // 6 warps 61.7 us, 7 warps 58.3 us, 8 warps (the register-file limit) 56.3 us; the cost-only
+  // kernel scales the same way.  MINSNAP_TUNE_MAX_WARPS overrides for measurements.
+  int cap = 8;
   if (const char* v = std::getenv("MINSNAP_TUNE_MAX_WARPS")) {
     const int want = std::atoi(v);
     if (want >= 1) cap = want;
   }
   if (warps == 1 && cap < 8) {
-    const size_t need = ((228 * 1024) / (size_t)cap - 1024) & ~(size_t)15;
+    // shared memory is carved in 256-byte units (ncu: padding to a multiple of 16 bytes that "fits" 7
+    // CTAs on paper leaves 6 resident)
+    const size_t need = ((228 * 1024) / (size_t)cap - 1024) & ~(size_t)255;
     if (need > smem && need <= kMaxDynamicSmem && (228 * 1024) / (need + 1024) == (size_t)cap) smem = need;
   }
   // the cost path is compiled out when no cost is requested (smaller hot loop, fewer registers)
