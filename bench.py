@@ -170,7 +170,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference needs Eigen3/glog/NLopt, absent from this image: its algorithm is timed through the oracle port",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -340,7 +340,7 @@ def run_gpu_arm(args):
                                        "(computeMaximumOfMagnitude)" % (B, K_SEG),
                       "nccl_gather_ms": gather_ms},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
         dist.destroy_process_group()
 
@@ -351,7 +351,26 @@ def ms_launches_per_step(ms):
     return 1 if getattr(ms.api, "STANDARD_FAST_ROUTE", False) else 4
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    # Libraries print to the C-level stdout behind Python's back (NCCL announces its version there):
+    # keep the original stdout for the JSON line only and send everything else to stderr.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
