@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "minsnap_standard_fast.cuh"
+#include "minsnap_standard_bcr.cuh"
 #include "minsnap_standard_ws.cuh"
 
 namespace minsnap {
@@ -93,7 +94,10 @@ static cudaError_t generic_route(long B, int S, int K, int D, int N, int derivat
   return launch_solve_general(g, stream);
 }
 
-bool standard_supported(int K, int D, int N, int derivative) { return fast::supported(K, D, N, derivative); }
+bool standard_supported(int K, int D, int N, int derivative) {
+  return fast::supported(K, D, N, derivative) ||
+         (N == 10 && derivative == 4 && D >= 1 && D <= 3 && K > fast::kMaxK && bcr::supported(K, D));
+}
 
 // Kernel choice for the fast route: the two-lane kernel (default) or the warp-specialised CTA
 // (MINSNAP_STANDARD_KERNEL=ws; correct, parity-tested, but measured slower on B200: its matrix
@@ -124,7 +128,10 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
   const double* times = a.d_times;
   cudaError_t e;
   const bool fast_ok = fast::supported(a.K, a.D, a.N, a.derivative);
-  if (!times && !fast_ok) {
+  // the reduction kernel covers long chains whose staged inputs no longer fit the two-lane kernel
+  const bool bcr_ok = a.N == 10 && a.derivative == 4 && a.D >= 1 && a.D <= 3 && a.K > fast::kMaxK &&
+                      bcr::supported(a.K, a.D);
+  if (!times && !fast_ok && !bcr_ok) {
     // the generic route needs the times in memory; the fast kernel computes them in-register
     double* dst = a.d_times_out;
     if (!dst) {
@@ -136,7 +143,7 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
       return e;
     times = dst;
   }
-  if (fast_ok) {
+  if (fast_ok || bcr_ok) {
     fast::FastParams p;
     p.B = a.B; p.K = a.K; p.positions = a.d_positions; p.end_derivatives = a.d_end_derivatives;
     p.times = a.d_times; p.v_max = a.v_max; p.a_max = a.a_max; p.magic = a.magic; p.times_out = a.d_times_out;
@@ -144,6 +151,29 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
     p.aligned16 = (reinterpret_cast<uintptr_t>(a.d_positions) % 16 == 0) &&
                   (reinterpret_cast<uintptr_t>(a.d_times) % 16 == 0) &&
                   (reinterpret_cast<uintptr_t>(a.d_coeffs) % 16 == 0);
+    // Long chains: block cyclic reduction, one CTA per trajectory (minsnap_standard_bcr.cuh), while
+    // the batch is too small to fill the machine with two-lane warps.  Measured at K = 256: a
+    // trajectory takes 35 us through the reduction and two CTAs fit an SM, so B trajectories cost
+    // ceil(B / 296) x 35 us (64 -> 0.035 ms, 512 -> 0.076 ms, 4,096 -> 0.52 ms); the two-lane kernel
+    // needs 0.23 ms however small the batch and 0.61 ms for 4,096, but keeps that time up to ~19,000
+    // trajectories (16 per warp, 8 warps per SM).  MINSNAP_LONG_CHAIN_KERNEL=pair|bcr forces one.
+    const char* which = a.K > fast::kMaxK ? std::getenv("MINSNAP_LONG_CHAIN_KERNEL") : nullptr;
+    const int forced = !which ? 0 : std::strcmp(which, "pair") == 0 ? 1 : std::strcmp(which, "bcr") == 0 ? 2 : 0;
+    const bool small_batch = a.B <= 148L * 2 * 16;
+    if (bcr_ok && (!fast_ok || (forced != 1 && (small_batch || forced == 2)))) {
+      double* cost = p.cost;
+      p.cost = nullptr;
+      if (cost && !p.times && !p.times_out) {
+        // the cost pass below reads the segment times the kernel computes
+        if ((e = times_scratch.alloc(sizeof(double) * (size_t)a.B * a.K, stream)) != cudaSuccess) return e;
+        p.times_out = static_cast<double*>(times_scratch.ptr);
+      }
+      if ((e = bcr::launch(p, a.D, stream)) != cudaSuccess) return e;
+      // a16 from the coefficients (ref computeCost, LIN.i:113-130)
+      if (cost)
+        return launch_cost(a.B, a.K, a.D, a.N, a.derivative, a.d_coeffs, p.times ? p.times : p.times_out, cost, stream);
+      return cudaSuccess;
+    }
     return launch_fast_route(p, a.D, true, use_ws_kernel(a.K, a.D, a.N, a.derivative), stream);
   }
   return generic_route(a.B, 1, a.K, a.D, a.N, a.derivative, a.d_positions, a.d_end_derivatives, times, a.d_coeffs,

@@ -270,6 +270,63 @@ def test_solve_standard_against_oracle(ms, oracle, torch_cuda, K, B):
     assert check_path(coeffs[B // 2], times[B // 2], mask, values[B // 2], oracle) < 1e-6
 
 
+@pytest.mark.parametrize("D", [1, 2, 3])
+def test_long_chain_kernels_agree(ms, oracle, torch_cuda, monkeypatch, D):
+    """K > 24 has two kernels: block cyclic reduction (one CTA per trajectory, small batches) and the
+    two-lane kernel with its blocks in global memory (large batches, K > 513).  Both are checked against
+    the oracle elsewhere (K = 25, 50, 101, 256 above; whichever kernel the batch size selects); here
+    they are checked against each other over chain lengths around every power of two, with non-zero
+    boundary derivatives, device-side segment times and all optional outputs."""
+    torch = torch_cuda
+    rng = np.random.default_rng(21 + D)
+    # the two-lane kernel stages the inputs of 16 trajectories in shared memory: K <= ~440 at D = 3
+    long_ks = [511, 512, 513] if D < 3 else [400, 440]
+    for K in list(range(25, 40)) + [63, 64, 65, 100, 127, 128, 129, 255, 256, 257, 300] + long_ks:
+        B = 5
+        pos = np.cumsum(rng.uniform(0.3, 2.0, (B, K + 1, D)) * rng.choice([-1.0, 1.0], (B, K + 1, D)), axis=1)
+        ends = rng.normal(size=(B, 2, 4, D))
+        outs = {}
+        for which in ("bcr", "pair"):
+            monkeypatch.setenv("MINSNAP_LONG_CHAIN_KERNEL", which)
+            outs[which] = ms.solve_standard(dev(torch, pos), None, end_derivatives=dev(torch, ends), v_max=3.0,
+                                            a_max=5.0, want_free=True, want_cost=True, want_times=True)
+        a, b = outs["bcr"], outs["pair"]
+        assert (a["status"] == 0).all() and (b["status"] == 0).all()
+        assert torch.equal(a["times"], b["times"])
+        assert coeff_rel_err(a["coeffs"].cpu().numpy(), b["coeffs"].cpu().numpy()) <= 1e-9, K
+        scale = b["free_values"].abs().amax(dim=(1, 2), keepdim=True)
+        assert float(((a["free_values"] - b["free_values"]).abs() / scale).max()) <= 1e-9, K
+        assert float((a["cost"] / b["cost"] - 1.0).abs().max()) <= 1e-9, K
+    monkeypatch.delenv("MINSNAP_LONG_CHAIN_KERNEL")
+    if D == 3:
+        # the reduction reaches K = 513 at D = 3 (the two-lane kernel does not): checked against the oracle
+        K = 513
+        pos, times = random_batch(oracle, 1, K)
+        out = ms.solve_standard(dev(torch, pos), dev(torch, times), want_cost=True)
+        ref = oracle_solve_batch(oracle, standard_mask(K), batch_values(pos), times)
+        assert coeff_rel_err(out["coeffs"].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
+        assert abs(float(out["cost"][0]) / ref["cost"][0] - 1.0) <= COST_TOL
+    if D == 1:
+        # chains beyond the reduction's thread budget (K > 513) fall back to the two-lane kernel
+        K = 600
+        pos, times = random_batch(oracle, 2, K, D=1)
+        out = ms.solve_standard(dev(torch, pos), dev(torch, times))
+        assert (out["status"] == 0).all()
+        mask, values = standard_mask(K), batch_values(pos)
+        assert check_path(out["coeffs"].cpu().numpy()[0], times[0], mask, values[0], oracle) < 1e-6
+
+
+def test_long_chain_status_bits(ms, oracle, torch_cuda):
+    torch = torch_cuda
+    K, B = 64, 4
+    pos, times = random_batch(oracle, B, K)
+    times[1, 10] = -1.0
+    out = ms.solve_standard(dev(torch, pos), dev(torch, times))
+    st = out["status"].cpu().numpy()
+    assert st[0] == 0 and st[2] == 0 and st[3] == 0
+    assert st[1] & 2                                              # MINSNAP_STATUS_BAD_TIME
+
+
 def test_solve_standard_nonzero_end_derivatives(ms, oracle, torch_cuda):
     torch = torch_cuda
     K, B = 10, 64
