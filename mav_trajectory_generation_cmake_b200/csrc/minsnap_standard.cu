@@ -154,12 +154,13 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
     // Long chains: block cyclic reduction, one CTA per trajectory (minsnap_standard_bcr.cuh), while
     // the batch is too small to fill the machine with two-lane warps.  Measured at K = 256: a
     // trajectory takes 35 us through the reduction and two CTAs fit an SM, so B trajectories cost
-    // ceil(B / 296) x 35 us (64 -> 0.035 ms, 512 -> 0.076 ms, 4,096 -> 0.52 ms); the two-lane kernel
-    // needs 0.23 ms however small the batch and 0.61 ms for 4,096, but keeps that time up to ~19,000
-    // trajectories (16 per warp, 8 warps per SM).  MINSNAP_LONG_CHAIN_KERNEL=pair|bcr forces one.
+    // ceil(B / 296) x 35 us (64 -> 0.035 ms, 512 -> 0.075 ms, 4,096 -> 0.52 ms); the two-lane kernel
+    // (sweeps, then the separate recovery pass below) needs 0.17 ms however small the batch and
+    // 0.48 ms for 4,096, and keeps that time up to ~19,000 trajectories (16 per warp, 8 warps per
+    // SM).  MINSNAP_LONG_CHAIN_KERNEL=pair|bcr forces one.
     const char* which = a.K > fast::kMaxK ? std::getenv("MINSNAP_LONG_CHAIN_KERNEL") : nullptr;
     const int forced = !which ? 0 : std::strcmp(which, "pair") == 0 ? 1 : std::strcmp(which, "bcr") == 0 ? 2 : 0;
-    const bool small_batch = a.B <= 148L * 2 * 16;
+    const bool small_batch = a.B <= 148L * 2 * 12;
     if (bcr_ok && (!fast_ok || (forced != 1 && (small_batch || forced == 2)))) {
       double* cost = p.cost;
       p.cost = nullptr;
@@ -172,6 +173,27 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
       // a16 from the coefficients (ref computeCost, LIN.i:113-130)
       if (cost)
         return launch_cost(a.B, a.K, a.D, a.N, a.derivative, a.d_coeffs, p.times ? p.times : p.times_out, cost, stream);
+      return cudaSuccess;
+    }
+    if (a.K > fast::kMaxK) {
+      // Two-lane kernel, long-chain mode: forward and backward sweeps only (free derivatives out), then
+      // the coefficients as a pass of their own with one thread per segment, then the cost from them.
+      AsyncBuffer free_scratch;
+      double* cost = p.cost;
+      p.cost = nullptr;
+      if (!p.free_out) {
+        if ((e = free_scratch.alloc(sizeof(double) * (size_t)a.B * (a.K - 1) * fast::kF * a.D, stream)) != cudaSuccess)
+          return e;
+        p.free_out = static_cast<double*>(free_scratch.ptr);
+      }
+      if (!p.times && !p.times_out) {
+        if ((e = times_scratch.alloc(sizeof(double) * (size_t)a.B * a.K, stream)) != cudaSuccess) return e;
+        p.times_out = static_cast<double*>(times_scratch.ptr);
+      }
+      if ((e = launch_fast_route(p, a.D, false, false, stream)) != cudaSuccess) return e;
+      const double* t = p.times ? p.times : p.times_out;
+      if ((e = bcr::launch_recover(p, a.D, p.free_out, t, stream)) != cudaSuccess) return e;
+      if (cost) return launch_cost(a.B, a.K, a.D, a.N, a.derivative, a.d_coeffs, t, cost, stream);
       return cudaSuccess;
     }
     return launch_fast_route(p, a.D, true, use_ws_kernel(a.K, a.D, a.N, a.derivative), stream);

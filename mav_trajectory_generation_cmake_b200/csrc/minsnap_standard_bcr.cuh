@@ -87,6 +87,88 @@ __device__ __forceinline__ int position(const Levels& L, int i) {
   return L.offset[l] + (i >> (l + 1));
 }
 
+// Coefficients of one segment (a13: c = A^-1 d with A^-1_T[i][r] = A1inv[i][r] T^(k_r - i)) from the
+// derivative vectors at its two vertices; the D polynomials leave as 32-byte stores on sector
+// boundaries.  Returns true when a coefficient is not finite.
+template <int D>
+__device__ __forceinline__ bool recover_segment(const double* pos_seg, double T, const double (&ds)[kF][D],
+                                                const double (&de)[kF][D], double* dst, bool aligned16) {
+  bool nonfinite = false;
+  const double T2 = T * T, T3 = T2 * T, T4 = T2 * T2;
+  const double tk[kF] = {T, T2, T3, T4};
+  const double i1 = fast::fast_rcp(T);
+  const double i2 = i1 * i1, i4 = i2 * i2, i5 = i4 * i1;
+  const double ipow[5] = {i5, i5 * i1, i5 * i2, i4 * i4, i4 * i5};   // T^-5 .. T^-9
+  double cf[D][kN];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double dp = pos_seg[D + d] - pos_seg[d];
+    cf[d][0] = pos_seg[d];
+#pragma unroll
+    for (int a = 0; a < kF; ++a) cf[d][1 + a] = A1T(1 + a, 1 + a) * ds[a][d];
+#pragma unroll
+    for (int i = 5; i < kN; ++i) {
+      double acc = A1T(i, 5) * dp;
+#pragma unroll
+      for (int a = 0; a < kF; ++a) {
+        acc = fma(A1T(i, 1 + a), tk[a] * ds[a][d], acc);
+        acc = fma(A1T(i, 6 + a), tk[a] * de[a][d], acc);
+      }
+      cf[d][i] = acc * ipow[i - 5];
+    }
+    const int e9 = __double2hiint(cf[d][kN - 1]) & 0x7ff00000, e4 = __double2hiint(cf[d][kF]) & 0x7ff00000;
+    if (e9 == 0x7ff00000 || e4 == 0x7ff00000) nonfinite = true;
+  }
+  constexpr int nn = D * kN;
+#define MINSNAP_CF(e) cf[(e) / kN][(e) % kN]
+  if (aligned16) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 16) == 0) {
+#pragma unroll
+      for (int e = 0; e + 4 <= nn; e += 4)
+        fast::store_cs_v4(dst + e, MINSNAP_CF(e), MINSNAP_CF(e + 1), MINSNAP_CF(e + 2), MINSNAP_CF(e + 3));
+      if (nn % 4 == 2) __stcs(reinterpret_cast<double2*>(dst + nn - 2), make_double2(MINSNAP_CF(nn - 2), MINSNAP_CF(nn - 1)));
+    } else {
+      __stcs(reinterpret_cast<double2*>(dst), make_double2(MINSNAP_CF(0), MINSNAP_CF(1)));
+#pragma unroll
+      for (int e = 2; e + 4 <= nn; e += 4)
+        fast::store_cs_v4(dst + e, MINSNAP_CF(e), MINSNAP_CF(e + 1), MINSNAP_CF(e + 2), MINSNAP_CF(e + 3));
+      if ((nn - 2) % 4 == 2)
+        __stcs(reinterpret_cast<double2*>(dst + nn - 2), make_double2(MINSNAP_CF(nn - 2), MINSNAP_CF(nn - 1)));
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < nn; ++e) __stcs(dst + e, MINSNAP_CF(e));
+  }
+#undef MINSNAP_CF
+  return nonfinite;
+}
+
+// Coefficient recovery as a pass of its own, one thread per (trajectory, segment), for the long-chain
+// mode of the two-lane kernel: its lanes would otherwise walk the K segments one after the other
+// (a third of the chain latency at K = 256).  free_values [B][K-1][kF][D] as the solve wrote them.
+template <int D>
+__global__ void __launch_bounds__(128) recover_standard_kernel(FastParams p, const double* __restrict__ free_values,
+                                                               const double* __restrict__ times) {
+  const int K = p.K, nb = K - 1;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.B * K) return;
+  const long b = idx / K;
+  const int seg = (int)(idx - b * K);
+  double ds[kF][D], de[kF][D];
+  const double* bd = p.end_derivatives ? p.end_derivatives + b * 2L * kF * D : nullptr;
+  const double* fv = free_values + b * (long)nb * kF * D;
+#pragma unroll
+  for (int a = 0; a < kF; ++a)
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      ds[a][d] = seg >= 1 ? fv[((seg - 1) * kF + a) * D + d] : (bd ? bd[a * D + d] : 0.0);
+      de[a][d] = seg + 1 <= nb ? fv[(seg * kF + a) * D + d] : (bd ? bd[kF * D + a * D + d] : 0.0);
+    }
+  const bool bad = recover_segment<D>(p.positions + (b * (K + 1) + seg) * D, times[idx], ds, de,
+                                      p.coeffs + idx * (D * kN), p.aligned16);
+  if (bad && p.status) atomicOr(p.status + b, 4);
+}
+
 template <int D>
 __global__ void __launch_bounds__(kMaxThreads) solve_standard_bcr_kernel(FastParams p) {
   extern __shared__ __align__(16) double smem[];
@@ -374,53 +456,8 @@ __global__ void __launch_bounds__(kMaxThreads) solve_standard_bcr_kernel(FastPar
             de[a][d] = seg + 1 <= nb ? rec[(kFieldBY + a * D + d) * nb + at_e] : bd_s[kF * D + a * D + d];
           }
       }
-      const double T2 = T * T, T3 = T2 * T, T4 = T2 * T2;
-      const double tk[kF] = {T, T2, T3, T4};
-      const double i1 = fast::fast_rcp(T);
-      const double i2 = i1 * i1, i4 = i2 * i2, i5 = i4 * i1;
-      const double ipow[5] = {i5, i5 * i1, i5 * i2, i4 * i4, i4 * i5};   // T^-5 .. T^-9
-      double cf[D][kN];
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const double dp = pos_s[(seg + 1) * D + d] - pos_s[seg * D + d];
-        cf[d][0] = pos_s[seg * D + d];
-#pragma unroll
-        for (int a = 0; a < kF; ++a) cf[d][1 + a] = A1T(1 + a, 1 + a) * ds[a][d];
-#pragma unroll
-        for (int i = 5; i < kN; ++i) {
-          double acc = A1T(i, 5) * dp;
-#pragma unroll
-          for (int a = 0; a < kF; ++a) {
-            acc = fma(A1T(i, 1 + a), tk[a] * ds[a][d], acc);
-            acc = fma(A1T(i, 6 + a), tk[a] * de[a][d], acc);
-          }
-          cf[d][i] = acc * ipow[i - 5];
-        }
-        const int e9 = __double2hiint(cf[d][kN - 1]) & 0x7ff00000, e4 = __double2hiint(cf[d][kF]) & 0x7ff00000;
-        if (e9 == 0x7ff00000 || e4 == 0x7ff00000) nonfinite = 1;
-      }
-      double* dst = p.coeffs + (b * (long)K + seg) * (D * kN);
-      constexpr int nn = D * kN;
-#define MINSNAP_CF(e) cf[(e) / kN][(e) % kN]
-      if (p.aligned16) {
-        if ((reinterpret_cast<uintptr_t>(dst) & 16) == 0) {
-#pragma unroll
-          for (int e = 0; e + 4 <= nn; e += 4)
-            fast::store_cs_v4(dst + e, MINSNAP_CF(e), MINSNAP_CF(e + 1), MINSNAP_CF(e + 2), MINSNAP_CF(e + 3));
-          if (nn % 4 == 2) __stcs(reinterpret_cast<double2*>(dst + nn - 2), make_double2(MINSNAP_CF(nn - 2), MINSNAP_CF(nn - 1)));
-        } else {
-          __stcs(reinterpret_cast<double2*>(dst), make_double2(MINSNAP_CF(0), MINSNAP_CF(1)));
-#pragma unroll
-          for (int e = 2; e + 4 <= nn; e += 4)
-            fast::store_cs_v4(dst + e, MINSNAP_CF(e), MINSNAP_CF(e + 1), MINSNAP_CF(e + 2), MINSNAP_CF(e + 3));
-          if ((nn - 2) % 4 == 2)
-            __stcs(reinterpret_cast<double2*>(dst + nn - 2), make_double2(MINSNAP_CF(nn - 2), MINSNAP_CF(nn - 1)));
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < nn; ++e) __stcs(dst + e, MINSNAP_CF(e));
-      }
-#undef MINSNAP_CF
+      if (recover_segment<D>(pos_s + seg * D, T, ds, de, p.coeffs + (b * (long)K + seg) * (D * kN), p.aligned16))
+        nonfinite = 1;
     }
     if (nonfinite) status |= 4;
     if (p.status) {
@@ -451,6 +488,19 @@ inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
   const long max_grid = 148L * 64;
   if (grid > max_grid) grid = max_grid;
   solve_standard_bcr_kernel<D><<<(int)grid, threads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_recover(const FastParams& p, int D, const double* free_values, const double* times,
+                                  cudaStream_t stream) {
+  const long n = p.B * p.K;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  switch (D) {
+    case 1: recover_standard_kernel<1><<<grid, 128, 0, stream>>>(p, free_values, times); break;
+    case 2: recover_standard_kernel<2><<<grid, 128, 0, stream>>>(p, free_values, times); break;
+    case 3: recover_standard_kernel<3><<<grid, 128, 0, stream>>>(p, free_values, times); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 
