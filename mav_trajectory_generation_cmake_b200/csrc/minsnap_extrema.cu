@@ -220,8 +220,12 @@ __device__ inline double magnitude_at(const double* seg, int D, int N, uint32_t 
 // trailing coefficients then treats like the reference's own zeros.
 template <int LEN>
 __global__ void __launch_bounds__(128) segment_extrema_kernel(ExtremaParams p) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.B * p.K) return;
+  const long tid_global = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid_global >= p.B * p.K) return;
+  // segment-major thread order: a warp holds the same segment of 32 trajectories (the first and last
+  // segments of a rest-to-rest trajectory have a different root structure from the inner ones, and
+  // lanes with similar work diverge less)
+  const long idx = (tid_global % p.B) * p.K + tid_global / p.B;
   const int N = p.N, D = p.D, k = p.derivative;
   const double* seg = p.coeffs + idx * D * N;
   const double T = p.times[idx];
