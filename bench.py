@@ -134,6 +134,37 @@ def cpu_solves_per_s(positions, times, n_threads, budget_s):
     return best, sample, 1.0 / per_solve_1t
 
 
+def parity_block(ms, torch, pos_h, times_h, n_threads, n_check=4096):
+    """parity checks run with every benchmark -- the CUDA path against the oracle on a
+    random subset of the benchmark batch (coefficients, cost, sampled derivatives, index map)."""
+    from oracle.oracle_py import Oracle, standard_mask
+    orc = Oracle("f64")
+    rng = np.random.default_rng(20261018)
+    idx = np.sort(rng.choice(len(pos_h), size=min(n_check, len(pos_h)), replace=False))
+    p, t = np.ascontiguousarray(pos_h[idx]), np.ascontiguousarray(times_h[idx])
+    ref_c, ref_cost, st = orc.solve_batch_standard(p, t, NCOEF, SNAP, 4, n_threads)
+    out = ms.solve_standard(torch.from_numpy(p).cuda(), torch.from_numpy(t).cuda(), want_cost=True)
+    c = out["coeffs"].cpu().numpy()
+    num = np.abs(c - ref_c).max(axis=-1)
+    den = np.abs(ref_c).max(axis=-1)
+    coeff_err = float((num / np.where(den == 0, 1.0, den)).max())
+    cost_err = float(np.abs(out["cost"].cpu().numpy() / ref_cost - 1.0).max())
+    n_s = 64
+    samples, ts = ms.sample_uniform(out["coeffs"][:n_s], torch.from_numpy(t[:n_s]).cuda(), 128, 5, want_times=True)
+    samples, ts = samples.cpu().numpy(), ts.cpu().numpy()
+    sample_err = max(float(np.abs(samples[b] - orc.trajectory_sample(ref_c[b], t[b], ts[b], 5)).max())
+                     for b in range(n_s))
+    mask = standard_mask(K_SEG, NCOEF)
+    col_ref, nf, npf = orc.reorder(NCOEF, K_SEG, mask)
+    col, counts = ms.reorder(torch.from_numpy(mask.reshape(1, -1)).cuda(), NCOEF, K_SEG)
+    index_ok = bool(np.array_equal(col.cpu().numpy()[0], col_ref)) and tuple(counts.cpu().numpy()[0]) == (nf, npf)
+    ok = st == 0 and int((out["status"] != 0).sum()) == 0 and coeff_err <= 1e-8 and cost_err <= 1e-8 and \
+        sample_err <= 1e-6 and index_ok
+    return {"ok": bool(ok), "n_checked": int(len(idx)), "coeff_rel_err": coeff_err, "cost_rel_err": cost_err,
+            "sample_abs_err": sample_err, "index_map_bit_exact": index_ok,
+            "bars": {"coeff_rel_err": 1e-8, "cost_rel_err": 1e-8, "sample_abs_err": 1e-6}}
+
+
 def run_reference_arm(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -312,6 +343,7 @@ def run_gpu_arm(args):
 
         cores = os.cpu_count() or 1
         cpu_value, cpu_sample, cpu_1t = cpu_solves_per_s(pos_h, times_pin.numpy(), cores, budget_s=15.0)
+        parity = parity_block(ms, torch, pos_h, times_pin.numpy(), cores)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -332,6 +364,7 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": BYTES_OUT * B, "steps": e2e_steps,
                     "api": "minsnap_solve_standard_host (pinned host buffers, chunked double-buffered copies)"},
             "clocks": sampler.summary(),
+            "parity": parity,
             "extra": {"samples_per_s": samples_per_s, "sample_ms": sample_ms,
                       "sample_hbm_frac": samples_per_s * 120.0 / 1e9 / hbm_peak,
                       "sample_shape": "%d trajectories x %d instants x (pos..snap) x 3" % (B, M),
