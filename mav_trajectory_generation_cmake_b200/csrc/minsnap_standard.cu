@@ -153,14 +153,14 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
                   (reinterpret_cast<uintptr_t>(a.d_coeffs) % 16 == 0);
     // Long chains: block cyclic reduction, one CTA per trajectory (minsnap_standard_bcr.cuh), while
     // the batch is too small to fill the machine with two-lane warps.  Measured at K = 256: a
-    // trajectory takes 35 us through the reduction and two CTAs fit an SM, so B trajectories cost
-    // ceil(B / 296) x 35 us (64 -> 0.035 ms, 512 -> 0.075 ms, 4,096 -> 0.52 ms); the two-lane kernel
+    // trajectory takes ~27 us through the reduction and two CTAs fit an SM, so B trajectories cost
+    // ceil(B / 296) x 27 us (64 -> 0.028 ms, 512 -> 0.059 ms, 4,096 -> 0.37 ms); the two-lane kernel
     // (sweeps, then the separate recovery pass below) needs 0.17 ms however small the batch and
     // 0.48 ms for 4,096, and keeps that time up to ~19,000 trajectories (16 per warp, 8 warps per
     // SM).  MINSNAP_LONG_CHAIN_KERNEL=pair|bcr forces one.
     const char* which = a.K > fast::kMaxK ? std::getenv("MINSNAP_LONG_CHAIN_KERNEL") : nullptr;
     const int forced = !which ? 0 : std::strcmp(which, "pair") == 0 ? 1 : std::strcmp(which, "bcr") == 0 ? 2 : 0;
-    const bool small_batch = a.B <= 148L * 2 * 12;
+    const bool small_batch = a.B <= 148L * 2 * 17;
     if (bcr_ok && (!fast_ok || (forced != 1 && (small_batch || forced == 2)))) {
       double* cost = p.cost;
       p.cost = nullptr;

@@ -23,8 +23,13 @@
 //
 // Shared memory per trajectory: 44 doubles per block (Q over D, P over R, y/x over b), stored
 // level-major so that the threads of a level touch consecutive words, plus the staged inputs:
-// K = 256 -> 98 KB, two CTAs per SM.  Coefficients: one thread per segment, 32-byte stores.
+// K = 256 -> 107 KB, two CTAs per SM.  Coefficients: one thread per segment, 32-byte stores.
+// Measured per trajectory (clock64, K = 256, one CTA per SM): inputs 3.5 k cycles (now prefetched with
+// cp.async during the previous trajectory), assembly 2.8 k, reduction 22.6 k (35.5 k before the
+// read-modify-writes of a phase were split into loads / arithmetic / stores), back substitution
+// 7.5 k, coefficients 5.7 k.
 #pragma once
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 
 #include "minsnap_device.cuh"
@@ -56,7 +61,8 @@ __host__ __device__ constexpr int record_doubles() { return 32 + kF * D; }
 template <int D>
 __host__ __device__ inline size_t smem_doubles(int K) {
   const size_t nb = K - 1;
-  return nb * record_doubles<D>() + (size_t)(K + 1) * D + K + 2 * kF * D;
+  // records + two input buffers (the next trajectory's inputs arrive while this one is solved)
+  return nb * record_doubles<D>() + 2 * ((size_t)(K + 1) * D + K + 2 * kF * D);
 }
 
 struct Levels {
@@ -175,24 +181,48 @@ __global__ void __launch_bounds__(kMaxThreads) solve_standard_bcr_kernel(FastPar
   const int K = p.K, nb = K - 1;
   const int tid = threadIdx.x;
   double* rec = smem;                                        // [44][nb]
-  double* pos_s = rec + (size_t)nb * record_doubles<D>();    // [K+1][D]
-  double* time_s = pos_s + (K + 1) * D;                      // [K]
-  double* bd_s = time_s + K;                                 // [2][kF][D] boundary derivatives
-  const Levels L = make_levels(nb);
+  const int in_doubles = (K + 1) * D + K + 2 * kF * D;       // positions, times, boundary derivatives
+  double* in_base = rec + (size_t)nb * record_doubles<D>();  // [2][in_doubles]
+  __shared__ Levels sL;
   __shared__ int s_status;
+  if (tid == 0) sL = make_levels(nb);
+  const Levels& L = sL;
+
+  // cp.async staging of one trajectory's inputs into buffer `which`
+  auto issue_inputs = [&](long b, int which) {
+    double* dst = in_base + (size_t)which * in_doubles;
+    const double* src_p = p.positions + b * (long)(K + 1) * D;
+    for (int e = tid; e < (K + 1) * D; e += blockDim.x) __pipeline_memcpy_async(dst + e, src_p + e, 8);
+    if (p.times) {
+      const double* src_t = p.times + b * (long)K;
+      for (int e = tid; e < K; e += blockDim.x) __pipeline_memcpy_async(dst + (K + 1) * D + e, src_t + e, 8);
+    }
+    if (p.end_derivatives) {
+      const double* src_b = p.end_derivatives + b * 2L * kF * D;
+      for (int e = tid; e < 2 * kF * D; e += blockDim.x) __pipeline_memcpy_async(dst + (K + 1) * D + K + e, src_b + e, 8);
+    }
+    __pipeline_commit();
+  };
+  int cur = 0;
+  if ((long)blockIdx.x < p.B) issue_inputs(blockIdx.x, 0);
 
   for (long b = blockIdx.x; b < p.B; b += gridDim.x) {
-    if (tid == 0) s_status = 0;
     // ---- inputs --------------------------------------------------------------------------------
-    for (int e = tid; e < (K + 1) * D; e += blockDim.x) pos_s[e] = p.positions[b * (long)(K + 1) * D + e];
-    for (int e = tid; e < 2 * kF * D; e += blockDim.x)
-      bd_s[e] = p.end_derivatives ? p.end_derivatives[b * 2L * kF * D + e] : 0.0;
+    __pipeline_wait_prior(0);
+    if (tid == 0) s_status = 0;
     __syncthreads();
+    if (b + gridDim.x < p.B) issue_inputs(b + gridDim.x, cur ^ 1);   // lands during this trajectory's solve
+    double* pos_s = in_base + (size_t)cur * in_doubles;     // [K+1][D]
+    double* time_s = pos_s + (K + 1) * D;                    // [K]
+    double* bd_s = time_s + K;                               // [2][kF][D] boundary derivatives
+    cur ^= 1;
+    if (!p.end_derivatives)
+      for (int e = tid; e < 2 * kF * D; e += blockDim.x) bd_s[e] = 0.0;
     int status = 0;
     for (int e = tid; e < K; e += blockDim.x) {
       double T;
       if (p.times) {
-        T = p.times[b * (long)K + e];
+        T = time_s[e];
       } else {
         // ref estimateSegmentTimes (src/vertex.cpp:162-178), same expression as minsnap_estimate_segment_times
         double s2 = 0.0;
@@ -203,9 +233,9 @@ __global__ void __launch_bounds__(kMaxThreads) solve_standard_bcr_kernel(FastPar
         const double distance = sqrt(s2);
         T = distance / p.v_max * 2 * (1.0 + p.magic * p.v_max / p.a_max * exp(-distance / p.v_max * 2));
         if (p.times_out) p.times_out[b * (long)K + e] = T;
+        time_s[e] = T;
       }
       if (!(T > 0.0)) status |= 2;
-      time_s[e] = T;
     }
     __syncthreads();
 
@@ -315,48 +345,70 @@ __global__ void __launch_bounds__(kMaxThreads) solve_standard_bcr_kernel(FastPar
           for (int a = 0; a < kF; ++a) y[a][d] = col[a];
         }
       }
-      // phase 1: right neighbours (D_m -= R_i^T P_i, b_m -= R_i^T y_i)
+      // phase 1: right neighbours (D_m -= R_i^T P_i, b_m -= R_i^T y_i).  All loads first, all stores
+      // last: interleaved read-modify-writes of the same shared array would be kept in program order.
       if (has_m) {
+        double Dm[10], bm[kF][D];
+#pragma unroll
+        for (int e = 0; e < 10; ++e) Dm[e] = rec[(kFieldDQ + e) * nb + at_m];
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) bm[a][d] = rec[(kFieldBY + a * D + d) * nb + at_m];
 #pragma unroll
         for (int a = 0; a < kF; ++a)
 #pragma unroll
           for (int c = 0; c <= a; ++c) {
-            double acc = rec[(kFieldDQ + tri(a, c)) * nb + at_m];
+            double acc = Dm[tri(a, c)];
 #pragma unroll
             for (int r = 0; r < kF; ++r) acc = fma(-R[r][a], P[r][c], acc);
-            rec[(kFieldDQ + tri(a, c)) * nb + at_m] = acc;
+            Dm[tri(a, c)] = acc;
           }
 #pragma unroll
         for (int a = 0; a < kF; ++a)
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            double acc = rec[(kFieldBY + a * D + d) * nb + at_m];
+            double acc = bm[a][d];
 #pragma unroll
             for (int r = 0; r < kF; ++r) acc = fma(-R[r][a], y[r][d], acc);
-            rec[(kFieldBY + a * D + d) * nb + at_m] = acc;
+            bm[a][d] = acc;
           }
+#pragma unroll
+        for (int e = 0; e < 10; ++e) rec[(kFieldDQ + e) * nb + at_m] = Dm[e];
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) rec[(kFieldBY + a * D + d) * nb + at_m] = bm[a][d];
       }
       __syncthreads();
       // phase 2: left neighbours (D_n -= R_n Q_i, b_n -= R_n y_i, R_n <- -R_n P_i), then the block's own record
       if (has_n) {
+        double Dn[10], bn[kF][D];
+#pragma unroll
+        for (int e = 0; e < 10; ++e) Dn[e] = rec[(kFieldDQ + e) * nb + at_n];
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) bn[a][d] = rec[(kFieldBY + a * D + d) * nb + at_n];
 #pragma unroll
         for (int a = 0; a < kF; ++a)
 #pragma unroll
           for (int c = 0; c <= a; ++c) {
-            double acc = rec[(kFieldDQ + tri(a, c)) * nb + at_n];
+            double acc = Dn[tri(a, c)];
 #pragma unroll
             for (int r = 0; r < kF; ++r) acc = fma(-Rn[a][r], Q[r][c], acc);
-            rec[(kFieldDQ + tri(a, c)) * nb + at_n] = acc;
+            Dn[tri(a, c)] = acc;
           }
 #pragma unroll
         for (int a = 0; a < kF; ++a)
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            double acc = rec[(kFieldBY + a * D + d) * nb + at_n];
+            double acc = bn[a][d];
 #pragma unroll
             for (int r = 0; r < kF; ++r) acc = fma(-Rn[a][r], y[r][d], acc);
-            rec[(kFieldBY + a * D + d) * nb + at_n] = acc;
+            bn[a][d] = acc;
           }
+        double Rnew[kF][kF];
 #pragma unroll
         for (int a = 0; a < kF; ++a)
 #pragma unroll
@@ -364,8 +416,18 @@ __global__ void __launch_bounds__(kMaxThreads) solve_standard_bcr_kernel(FastPar
             double acc = 0.0;
 #pragma unroll
             for (int r = 0; r < kF; ++r) acc = fma(-Rn[a][r], P[r][c], acc);
-            rec[(kFieldRP + a * kF + c) * nb + at_n] = has_m ? acc : 0.0;
+            Rnew[a][c] = has_m ? acc : 0.0;
           }
+#pragma unroll
+        for (int e = 0; e < 10; ++e) rec[(kFieldDQ + e) * nb + at_n] = Dn[e];
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) rec[(kFieldBY + a * D + d) * nb + at_n] = bn[a][d];
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int c = 0; c < kF; ++c) rec[(kFieldRP + a * kF + c) * nb + at_n] = Rnew[a][c];
       }
       if (work) {
 #pragma unroll
