@@ -546,9 +546,10 @@ inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
   const size_t smem = smem_doubles<D>(p.K) * sizeof(double);
   cudaError_t e = cudaFuncSetAttribute(solve_standard_bcr_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  long grid = p.B;
-  const long max_grid = 148L * 64;
-  if (grid > max_grid) grid = max_grid;
+  // persistent CTAs, as many as are resident at once: each walks its trajectories with the next
+  // one's inputs in flight (a CTA per trajectory would leave the cp.async prefetch nothing to fetch)
+  const long resident = 148L * (kMaxDynamicSmem + 1024 >= 2 * (smem + 1024) ? 2 : 1);
+  long grid = p.B < resident ? p.B : resident;
   solve_standard_bcr_kernel<D><<<(int)grid, threads, smem, stream>>>(p);
   return cudaGetLastError();
 }
