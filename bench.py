@@ -207,6 +207,24 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+def bind_to_gpu_cpus(local):
+    """Run this rank on the host cores (and so allocate its pinned buffers on the NUMA node) next to
+    its GPU: with 8 ranks on a two-socket host the e2e copies otherwise cross the socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + bit for w, mask in enumerate(words) for bit in range(64) if (mask >> bit) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -216,6 +234,7 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the GPU arm has no CPU fallback")
     torch.cuda.set_device(local)
+    n_local_cpus = bind_to_gpu_cpus(local)
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -362,7 +381,8 @@ def run_gpu_arm(args):
                                        % (cpu_sample, cpu_1t)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BYTES_IN * B,
                     "d2h_bytes_per_step": BYTES_OUT * B, "steps": e2e_steps,
-                    "api": "minsnap_solve_standard_host (pinned host buffers, chunked double-buffered copies)"},
+                    "api": "minsnap_solve_standard_host (pinned host buffers, chunked double-buffered copies)",
+                    "host_cpus_bound": n_local_cpus},
             "clocks": sampler.summary(),
             "parity": parity,
             "extra": {"samples_per_s": samples_per_s, "sample_ms": sample_ms,

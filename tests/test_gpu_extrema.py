@@ -221,3 +221,22 @@ def test_extrema_full_size_properties(ms, oracle, torch_cuda):
     sl = slice(1000, 1032)
     got = to_host({kk: v[sl] for kk, v in ms.extrema(coeffs, times, 1, mode=0).items()})
     check_against_oracle(oracle, coeffs[sl].cpu().numpy(), times[sl].cpu().numpy(), got, 1, 0)
+
+
+@pytest.mark.parametrize("N,K,D", [(4, 1, 1), (4, 3, 2), (6, 1, 3), (10, 1, 3), (12, 2, 1)])
+def test_extrema_small_shapes_and_high_derivatives(ms, oracle, torch_cuda, N, K, D):
+    """Single segments, one dimension, the lowest polynomial order, and every derivative up to N - 2
+    (where the candidate polynomial is linear or constant)."""
+    torch = torch_cuda
+    rng = np.random.default_rng(7 * N + K + D)
+    B = 16
+    c = rng.uniform(-5.0, 5.0, (B, K, D, N))
+    c[0] = 0.0                                   # the zero trajectory
+    c[1, :, :, 1:] = 0.0                         # constants: no roots at any derivative
+    times = rng.uniform(0.5, 2.0, (B, K))
+    cd, td = torch.from_numpy(c).cuda(), torch.from_numpy(times).cuda()
+    for k in range(0, N - 1):
+        for mode in (0, 1):
+            got = to_host(ms.extrema(cd, td, k, mode=mode, want_roots=True))
+            check_against_oracle(oracle, c, times, got, k, mode)
+    assert ms.extrema_max_roots(N, N - 2, D) == (1 if D > 1 else 0)
