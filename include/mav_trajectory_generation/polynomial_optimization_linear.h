@@ -538,6 +538,23 @@ class PolynomialOptimizationBatch {
   const std::vector<double>& coefficients() const { return coeffs_; }   // [B][K][D][N]
   const std::vector<double>& segmentTimes() const { return times_; }   // [B][K]
 
+  // Largest magnitude of a derivative of every solved trajectory in one launch: what a loop over
+  // PolynomialOptimization<N>::computeMaximumOfMagnitude<Derivative>(nullptr) would return (ref LIN.i:470-503).
+  template <int Derivative>
+  std::vector<Extremum> computeMaximumOfMagnitude() const {
+    static_assert(N - Derivative - 1 > 0, "N-Derivative-1 has to be greater 0");
+    std::vector<Extremum> result(static_cast<size_t>(B_));
+    if (B_ == 0) return result;
+    std::vector<double> time(static_cast<size_t>(B_)), value(static_cast<size_t>(B_));
+    std::vector<int32_t> segment(static_cast<size_t>(B_));
+    gpu::check(minsnap_extrema_host(B_, K_, D_, N, coeffs_.data(), times_.data(), Derivative,
+                                    gpu::extremaMode(MINSNAP_EXTREMA_OPTIMIZATION), 0, time.data(), value.data(),
+                                    segment.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr),
+               "minsnap_extrema_host");
+    for (size_t b = 0; b < result.size(); ++b) result[b] = Extremum(time[b], value[b], segment[b]);
+    return result;
+  }
+
   void getTrajectory(long b, Trajectory* trajectory) const {
     CHECK_NOTNULL(trajectory);
     Segment::Vector segments(static_cast<size_t>(K_), Segment(N, D_));

@@ -430,6 +430,21 @@ static void testExtremaOfMagnitude(int D, int n_segments, size_t seed) {
                                                       seg_candidates, &s_min, &s_max));
   EXPECT_LT(std::fabs(s_max.value - t_max.value), 1e-9);
   gpu::keepSmallCoefficients(false);
+  // the additive batch class reports the same maximum for the same problem
+  if (D == 3) {
+    std::vector<double> flat;
+    for (const Vertex& v : vertices) {
+      Eigen::VectorXd pos;
+      v.getConstraint(derivative_order::POSITION, &pos);
+      for (int d = 0; d < D; ++d) flat.push_back(pos[d]);
+    }
+    PolynomialOptimizationBatch<N> batch(D, n_segments);
+    batch.solve(flat, segment_times);
+    const std::vector<Extremum> maxima = batch.computeMaximumOfMagnitude<derivative_order::VELOCITY>();
+    EXPECT_EQ(maxima.size(), static_cast<size_t>(1));
+    EXPECT_LT(std::fabs(maxima[0].value - v_max.value), 1e-9 * v_max.value);
+    EXPECT_EQ(maxima[0].segment_idx, v_max.segment_idx);
+  }
   // reference-compatible mode: never above the exact maximum
   const Extremum v_compat = opt.computeMaximumOfMagnitude<derivative_order::VELOCITY>(nullptr);
   EXPECT_TRUE(v_compat.value <= v_max.value * (1 + 1e-12));
