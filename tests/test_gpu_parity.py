@@ -625,3 +625,45 @@ def test_warp_specialised_variant_parity(ms, oracle, torch_cuda, monkeypatch):
     assert coeff_rel_err(out["coeffs"].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
     assert coeff_rel_err(out["coeffs"].cpu().numpy(), pair["coeffs"].cpu().numpy()) <= 1e-9
     assert np.abs(out["cost"].cpu().numpy() / ref["cost"] - 1.0).max() <= COST_TOL
+
+
+def test_randomised_shapes_fast_route_vs_general_route(ms, torch_cuda):
+    """120 random (K, D, B) shapes, boundary derivatives and time sources: the standard-mask kernels (two-lane,
+    cyclic reduction) against the general banded kernel, two independent implementations of the same algebra
+    that are each checked against the oracle elsewhere."""
+    torch = torch_cuda
+    rng = np.random.default_rng(20261018)
+    worst = 0.0
+    for trial in range(120):
+        K = int(rng.integers(1, 41))
+        D = int(rng.integers(1, 4))
+        B = int(rng.integers(1, 70))
+        pos = np.cumsum(rng.uniform(0.4, 3.0, (B, K + 1, D)) * rng.choice([-1.0, 1.0], (B, K + 1, D)), axis=1)
+        ends = rng.normal(size=(B, 2, 4, D)) if trial % 3 else None
+        pos_d = dev(torch, pos)
+        if trial % 2:
+            times = ms.estimate_segment_times(pos_d, 2.0 + 3.0 * rng.random(), 2.0 + 4.0 * rng.random())
+            fast = ms.solve_standard(pos_d, times, end_derivatives=None if ends is None else dev(torch, ends),
+                                     want_free=True, want_cost=True)
+        else:
+            v, a = 2.0 + 3.0 * rng.random(), 2.0 + 4.0 * rng.random()
+            fast = ms.solve_standard(pos_d, None, end_derivatives=None if ends is None else dev(torch, ends), v_max=v,
+                                     a_max=a, want_free=True, want_cost=True, want_times=True)
+            times = fast["times"]
+        mask = standard_mask(K)
+        values = np.zeros((B, K + 1, 5, D))
+        values[:, :, 0, :] = pos
+        if ends is not None:
+            values[:, 0, 1:, :] = ends[:, 0]
+            values[:, K, 1:, :] = ends[:, 1]
+        fixed = np.stack([compact_fixed(mask, v_) for v_ in values])
+        gen = ms.solve(mask, dev(torch, fixed), times)
+        assert (fast["status"] == 0).all() and (gen["status"] == 0).all(), (trial, K, D, B)
+        err = coeff_rel_err(fast["coeffs"].cpu().numpy(), gen["coeffs"].cpu().numpy())
+        worst = max(worst, err)
+        assert err <= 1e-8, (trial, K, D, B, err)
+        assert float((fast["cost"] / gen["cost"] - 1.0).abs().max()) <= 1e-8, (trial, K, D, B)
+        if K > 1:
+            scale = gen["free_values"].abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-300)
+            assert float(((fast["free_values"] - gen["free_values"]).abs() / scale).max()) <= 1e-8, (trial, K, D, B)
+    assert worst > 0.0
