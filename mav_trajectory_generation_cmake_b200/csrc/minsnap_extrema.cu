@@ -85,6 +85,16 @@ __device__ __forceinline__ void poly_value_slope(const double (&d)[DEG + 1], dou
   fp = b;
 }
 
+// 1/x to ~40 bits (hardware seed + one Newton step): a Newton or secant step does not need a correctly
+// rounded quotient -- an inexact step is corrected by the next one, and the bracket logic below catches
+// anything wild (a flushed subnormal slope gives inf, which falls back to bisection).  The IEEE division
+// it replaces is a ~20-instruction sequence per Newton iteration.
+__device__ __forceinline__ double quick_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return fma(r, fma(-x, r, 1.0), r);
+}
+
 // One root of a monotone piece: f(lo) and f(hi) have opposite signs.  Starts from the secant
 // point of the bracket, then Newton, with bisection whenever the step leaves the bracket.  Stops
 // when |f| is inside the rounding error of its own evaluation (bound taken at the starting point;
@@ -97,7 +107,7 @@ template <int DEG>
 __device__ __forceinline__ double refine_bracket(const double (&d)[DEG + 1], double lo, double hi, double f_lo,
                                                  double f_hi, double rel_tol) {
   const bool lo_negative = f_lo < 0.0;
-  double x = lo - f_lo * ((hi - lo) / (f_hi - f_lo));
+  double x = lo - f_lo * ((hi - lo) * quick_rcp(f_hi - f_lo));
   if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
   double f_noise = 0.0;
   for (int it = 0; it < 64; ++it) {
@@ -111,7 +121,7 @@ __device__ __forceinline__ double refine_bracket(const double (&d)[DEG + 1], dou
     }
     if (fabs(f) <= f_noise) return x;
     if ((f < 0.0) == lo_negative) lo = x; else hi = x;
-    double next = fp != 0.0 ? x - f / fp : lo - 1.0;
+    double next = fp != 0.0 ? fma(-f, quick_rcp(fp), x) : lo - 1.0;
     if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);
     if (next == lo || next == hi) return next;
     if (fabs(next - x) <= rel_tol * fabs(next)) return next;
