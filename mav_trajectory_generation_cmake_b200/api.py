@@ -1,6 +1,9 @@
 """Python plumbing over the C ABI: torch tensors for device memory and streams, numpy arrays
 for the host-buffer entry points.  Every function is a thin argument marshaller around one
-C-ABI call -- there is no arithmetic and no fallback here.
+C-ABI call -- there is no arithmetic and no fallback here.  The two additive drivers of the
+time-only problem (optimize_segment_times, time_objective_with_soft_constraints) are the
+exception: they chain several C-ABI calls on the device and glue them with elementwise torch
+operations (step ladders, exp / clamp of the soft-constraint terms).
 
 Layouts are those of include/minsnap_b200.h (h = N/2):
   fixed_values [B][n_fixed][D], free_values [B][n_free][D], positions [B][K+1][D],
@@ -246,6 +249,45 @@ def time_objective(positions, times, time_penalty, end_derivatives=None, N=10, d
                                              _dptr(end_derivatives), _dptr(times, torch.float64), float(time_penalty),
                                              _dptr(out), _dptr(cost_t), None, _stream()), "minsnap_time_objective")
     return (out, cost_t) if want_cost else out
+
+
+def time_objective_with_soft_constraints(positions, times, time_penalty, constraints, soft_constraint_weight=100.0,
+                                         maximum_cost=1.0e12, end_derivatives=None, N=10, derivative=SNAP,
+                                         want_terms=False):
+    """The reference's time-only objective with its soft limits on the magnitude of derivatives
+    (objectiveFunctionTime with use_soft_constraints, NL.i:765-832; evaluateMaximumMagnitudeAsSoftConstraint,
+    NL.i:2396-2426; evaluateMaximumMagnitudeConstraint, NL.i:2346-2392):
+
+        objective = computeCost + time_penalty * total_time^2
+                    + sum over constraints min(maximum_cost, exp((max |p^(k)| - limit) / limit * weight))
+
+    constraints: iterable of (derivative k, limit), e.g. [(1, v_max), (2, a_max)].  positions [B][K+1][D],
+    times [B][S][K] -> objective [B][S].  Composition of three C-ABI calls per constraint set: one solve of the
+    B * S allocations with coefficients, one minsnap_extrema per constraint (computeMaximumOfMagnitude
+    semantics), one fused epilogue on the device."""
+    torch = _torch()
+    B, K1, D = positions.shape
+    K = K1 - 1
+    S = times.shape[1]
+    flat_t = times.reshape(B * S, K).contiguous()
+    rep_p = positions.repeat_interleave(S, dim=0).contiguous()
+    rep_e = None if end_derivatives is None else end_derivatives.repeat_interleave(S, dim=0).contiguous()
+    sol = solve_standard(rep_p, flat_t, end_derivatives=rep_e, N=N, derivative=derivative, want_cost=True,
+                         want_status=False)
+    total = flat_t.sum(1)
+    cost_time = total * total * time_penalty
+    terms = []
+    for k, limit in constraints:
+        peak = extrema(sol["coeffs"], flat_t, int(k), mode=EXTREMA_OPTIMIZATION)["max_value"]
+        terms.append(torch.exp((peak - limit) / limit * soft_constraint_weight).clamp_max(maximum_cost))
+    obj = sol["cost"] + cost_time
+    for t in terms:
+        obj = obj + t
+    obj = obj.reshape(B, S)
+    if want_terms:
+        return obj, dict(cost_trajectory=sol["cost"].reshape(B, S), cost_time=cost_time.reshape(B, S),
+                         cost_constraints=[t.reshape(B, S) for t in terms])
+    return obj
 
 
 def time_gradient(coeffs, times, increment=0.1, w_d=0.1, w_t=1.0, derivative=SNAP, want_segment_cost=False):

@@ -138,3 +138,36 @@ def test_batched_time_descent(ms, oracle, torch_cuda):
     for b in (0, 17, 255):
         want, _ = oracle_objective(oracle, pos[b], t1h[b], penalty)
         assert abs(hist[-1, b] - want) <= COST_TOL * want
+
+
+def test_time_objective_with_soft_constraints(ms, oracle, torch_cuda):
+    """ref objectiveFunctionTime with use_soft_constraints (NL.i:765-832, 2346-2426): the soft term is
+    min(max_cost, exp(relative violation * weight)) per limited derivative, with the maximum of
+    computeMaximumOfMagnitude."""
+    torch = torch_cuda
+    B, S, K, penalty, weight = 6, 4, 10, 500.0, 100.0
+    pos, times = random_batch(oracle, B, K)
+    rng = np.random.default_rng(9)
+    cand = times[:, None, :] * rng.uniform(0.7, 1.5, (B, S, K))
+    limits = [(1, 4.0), (2, 2.0)]
+    obj, parts = ms.time_objective_with_soft_constraints(torch.from_numpy(pos).cuda(), torch.from_numpy(cand).cuda(),
+                                                         penalty, limits, soft_constraint_weight=weight,
+                                                         want_terms=True)
+    obj = obj.cpu().numpy()
+    for b in range(B):
+        for s in range(S):
+            r = oracle.solve(10, K, 3, 4, standard_mask(K), vertex_values(pos[b]), cand[b, s])
+            base, _ = oracle_objective(oracle, pos[b], cand[b, s], penalty)
+            want = base
+            for j, (k, limit) in enumerate(limits):
+                peak = float(oracle.minmax_magnitude(np.asarray(r["coeffs"], np.float64), cand[b, s], k, 0)["max"][1])
+                term = min(1.0e12, np.exp((peak - limit) / limit * weight))
+                got_term = float(parts["cost_constraints"][j][b, s])
+                assert abs(got_term - term) <= 1e-6 * term, (b, s, k, got_term, term)
+                want += term
+            assert abs(obj[b, s] - want) <= 1e-6 * want
+    # saturation at maximum_cost
+    sat = ms.time_objective_with_soft_constraints(torch.from_numpy(pos).cuda(), torch.from_numpy(cand).cuda(),
+                                                  penalty, [(1, 0.01)], soft_constraint_weight=weight, maximum_cost=7.0,
+                                                  want_terms=True)[1]["cost_constraints"][0]
+    assert float(sat.max()) == 7.0 and float(sat.min()) == 7.0
