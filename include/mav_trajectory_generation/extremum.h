@@ -1,6 +1,7 @@
-// Extremum: where and how large a derivative's magnitude gets (mirror of ref
-// include/mav_trajectory_generation/extremum.h:27-49).  `time` is relative to the start of the
-// segment `segment_idx`; ordering compares the values only.
+// Extremum: where and how large the magnitude of a derivative gets.  API mirror of the reference's
+// include/mav_trajectory_generation/extremum.h:27-49 (same member names, ordering by value only, same
+// printed form); produced by minsnap_extrema[_host] through Segment / Trajectory /
+// PolynomialOptimization.
 #ifndef MAV_TRAJECTORY_GENERATION_EXTREMUM_H_
 #define MAV_TRAJECTORY_GENERATION_EXTREMUM_H_
 
@@ -9,19 +10,24 @@
 namespace mav_trajectory_generation {
 
 struct Extremum {
+  // seconds since the start of segment `segment_idx`
   double time = 0.0;
+  // |p^(k)| there
   double value = 0.0;
   int segment_idx = 0;
 
   Extremum() = default;
-  Extremum(double _time, double _value, int _segment_idx) : time(_time), value(_value), segment_idx(_segment_idx) {}
-
-  bool operator<(const Extremum& rhs) const { return value < rhs.value; }
-  bool operator>(const Extremum& rhs) const { return value > rhs.value; }
+  Extremum(double at_time, double magnitude, int segment) : time(at_time), value(magnitude), segment_idx(segment) {}
 };
 
-inline std::ostream& operator<<(std::ostream& stream, const Extremum& e) {
-  return stream << "time: " << e.time << ", value: " << e.value << ", segment idx: " << e.segment_idx << std::endl;
+// Extrema compare by magnitude alone: the fold "a later candidate wins only when strictly larger" of
+// computeMaximumOfMagnitude / computeMinMaxMagnitude is written with these.
+inline bool operator<(const Extremum& a, const Extremum& b) { return a.value < b.value; }
+inline bool operator>(const Extremum& a, const Extremum& b) { return b < a; }
+
+inline std::ostream& operator<<(std::ostream& os, const Extremum& e) {
+  os << "time: " << e.time << ", value: " << e.value << ", segment idx: " << e.segment_idx << '\n';
+  return os.flush();
 }
 
 }  // namespace mav_trajectory_generation
