@@ -39,3 +39,84 @@ def gather_to_rank0(local, total, dist, dst=0):
         return out
     dist.gather(padded, None, dst=dst)
     return None
+
+
+class PeerGatherBuffer:
+    """A device buffer on rank `dst` that every rank of the node can STORE into over NVLink / NVSwitch
+    (CUDA IPC peer mapping), so that the solve kernel itself delivers its coefficient block to the
+    collecting GPU: pass `view(rank)` as the `coeffs` argument of solve_standard and the kernel's
+    32-byte stores go straight to the peer -- the gather of SURVEY.md section 8e without a separate
+    collective and without an intermediate copy.  One process per GPU, single node.
+
+    The buffer is one cudaMalloc on `dst` (not a slice of torch's caching allocator: an IPC handle
+    names a whole allocation).  `finish()` is the only synchronisation a consumer needs: a barrier
+    after every rank's stream has drained."""
+
+    def __init__(self, dist, rows_per_rank, row_shape, dtype, dst=0):
+        import numpy as np
+        import torch
+        from cuda.bindings import runtime as rt
+        self._rt, self._torch, self._dist = rt, torch, dist
+        self.rank, self.world, self.dst = dist.get_rank(), dist.get_world_size(), dst
+        self.rows, self.row_shape, self.dtype = rows_per_rank, tuple(row_shape), dtype
+        self.row_elems = int(np.prod(self.row_shape))
+        self.itemsize = torch.empty((), dtype=dtype).element_size()
+        self.bytes = self.world * rows_per_rank * self.row_elems * self.itemsize
+        self._owner = self.rank == dst
+        handle_bytes = [None]
+        if self._owner:
+            err, ptr = rt.cudaMalloc(self.bytes)
+            self._check(err, "cudaMalloc")
+            err, handle = rt.cudaIpcGetMemHandle(ptr)
+            self._check(err, "cudaIpcGetMemHandle")
+            handle_bytes = [bytes(handle.reserved)]
+            self.ptr = int(ptr)
+        dist.broadcast_object_list(handle_bytes, src=dst)
+        if not self._owner:
+            handle = rt.cudaIpcMemHandle_t()
+            handle.reserved = handle_bytes[0]
+            err, ptr = rt.cudaIpcOpenMemHandle(handle, rt.cudaIpcMemLazyEnablePeerAccess)
+            self._check(err, "cudaIpcOpenMemHandle")
+            self.ptr = int(ptr)
+
+    @staticmethod
+    def _check(err, what):
+        if int(err) != 0:
+            raise RuntimeError("%s failed: %s" % (what, err))
+
+    def _wrap(self, offset_bytes, shape):
+        torch = self._torch
+        typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4"}[self.dtype]
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (self.ptr + offset_bytes, False),
+                                        "version": 3, "strides": None}
+        t = torch.as_tensor(raw, device="cuda")
+        t._peer_buffer_keepalive = self
+        return t
+
+    def view(self, rank=None):
+        """The block of `rank` (default: this rank) inside the peer buffer, as a CUDA tensor."""
+        r = self.rank if rank is None else rank
+        block = self.rows * self.row_elems * self.itemsize
+        return self._wrap(r * block, (self.rows,) + self.row_shape)
+
+    def whole(self):
+        """All blocks, rank-major (meaningful on the owner after finish())."""
+        return self._wrap(0, (self.world * self.rows,) + self.row_shape)
+
+    def finish(self):
+        self._torch.cuda.synchronize()
+        self._dist.barrier()
+
+    def close(self):
+        rt = self._rt
+        self._torch.cuda.synchronize()
+        self._dist.barrier()
+        if self._owner:
+            rt.cudaFree(self.ptr)
+        else:
+            rt.cudaIpcCloseMemHandle(self.ptr)
+        self.ptr = 0
