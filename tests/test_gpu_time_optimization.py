@@ -13,37 +13,10 @@ forms R through A^-T Q A^-1, accurate to ~1e-10, and the central difference divi
 import numpy as np
 import pytest
 
-from helpers import COST_TOL, random_batch, standard_mask, vertex_values
+from helpers import (COST_TOL, oracle_gradient, oracle_objective, random_batch, standard_mask,
+                     vertex_values)
 
 pytestmark = pytest.mark.gpu
-
-
-def oracle_objective(oracle, pos, times, penalty):
-    K = times.shape[0]
-    r = oracle.solve(10, K, pos.shape[1], 4, standard_mask(K), vertex_values(pos), times)
-    total = 0.0
-    for t in times:
-        total += t
-    return float(r["cost"]) + total * total * penalty, float(r["cost"])
-
-
-def oracle_gradient(oracle, pos, times, increment, w_d, w_t):
-    K, D = times.shape[0], pos.shape[1]
-    mask, vals = standard_mask(K), vertex_values(pos)
-    base = oracle.solve(10, K, D, 4, mask, vals, times)
-    d_all = np.concatenate([base["d_fixed"], base["d_free"]], axis=1)   # [D][n_fixed + n_free]
-
-    def J_d(t):
-        R = oracle.solve(10, K, D, 4, mask, vals, t, want_R=True)["R"]
-        return float(sum(d_all[k] @ R @ d_all[k] for k in range(D)))
-
-    grad = np.zeros(K)
-    for n in range(K):
-        smaller, bigger = times.copy(), times.copy()
-        smaller[n] = 0.1 if smaller[n] <= 0.1 else smaller[n] - increment
-        bigger[n] = 0.1 if bigger[n] <= 0.1 else bigger[n] + increment
-        grad[n] = w_d * (J_d(bigger) - J_d(smaller)) / (2.0 * increment) + w_t
-    return grad, J_d(times)
 
 
 @pytest.mark.parametrize("K", [4, 10])
