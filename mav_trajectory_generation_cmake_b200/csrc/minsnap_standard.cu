@@ -153,8 +153,8 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
                   (reinterpret_cast<uintptr_t>(a.d_coeffs) % 16 == 0);
     // Long chains: block cyclic reduction, one CTA per trajectory (minsnap_standard_bcr.cuh), while
     // the batch is too small to fill the machine with two-lane warps.  Measured at K = 256: a
-    // trajectory takes ~27 us through the reduction and two CTAs fit an SM, so B trajectories cost
-    // ceil(B / 296) x 27 us (64 -> 0.028 ms, 512 -> 0.059 ms, 4,096 -> 0.37 ms); the two-lane kernel
+    // trajectory takes ~25 us through the reduction and two CTAs fit an SM, so B trajectories cost
+    // ceil(B / 296) x 25 us (64 -> 0.023 ms, 512 -> 0.052 ms, 4,096 -> 0.35 ms); the two-lane kernel
     // (sweeps, then the separate recovery pass below) needs 0.17 ms however small the batch and
     // 0.48 ms for 4,096, and keeps that time up to ~19,000 trajectories (16 per warp, 8 warps per
     // SM).  MINSNAP_LONG_CHAIN_KERNEL=pair|bcr forces one.

@@ -29,11 +29,11 @@ B, K = 4096, 256
 pos = torch.from_numpy(ms.random_positions_host(B, K, LO, HI, 12345)).cuda()
 times = ms.estimate_segment_times(pos, 3.0, 5.0)
 coeffs4 = torch.empty((B, K, 3, 10), dtype=torch.float64, device="cuda")
-ms_ = timeit(lambda: ms.solve_standard(pos, times, coeffs=coeffs4, want_status=False), steps=5, warm=2)
+ms_ = timeit(lambda: ms.solve_standard(pos, times, coeffs=coeffs4, want_status=False), steps=20, warm=3)
 print("config4 long horizon: %d x K=%d  %.3f ms/batch  %.1f k solves/s  (HBM floor %.3f ms, FP64 floor %.3f ms)"
       % (B, K, ms_, B / ms_, B * 69656 / 6547.8e9 * 1e3, B * 239936 / 36.8e12 * 1e3))
 for Bs in (512, 64):
-    ms_ = timeit(lambda: ms.solve_standard(pos[:Bs], times[:Bs], coeffs=coeffs4[:Bs], want_status=False), steps=5, warm=2)
+    ms_ = timeit(lambda: ms.solve_standard(pos[:Bs], times[:Bs], coeffs=coeffs4[:Bs], want_status=False), steps=50, warm=5)
     print("config4 shard of %d trajectories (8-GPU share = 512): %.3f ms" % (Bs, ms_))
 del coeffs4
 
