@@ -160,7 +160,7 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
     // SM).  MINSNAP_LONG_CHAIN_KERNEL=pair|bcr forces one.
     const char* which = a.K > fast::kMaxK ? std::getenv("MINSNAP_LONG_CHAIN_KERNEL") : nullptr;
     const int forced = !which ? 0 : std::strcmp(which, "pair") == 0 ? 1 : std::strcmp(which, "bcr") == 0 ? 2 : 0;
-    const bool small_batch = a.B <= 148L * 2 * 17;
+    const bool small_batch = a.B <= 148L * 2 * 19;
     if (bcr_ok && (!fast_ok || (forced != 1 && (small_batch || forced == 2)))) {
       double* cost = p.cost;
       p.cost = nullptr;
