@@ -60,8 +60,8 @@ __host__ __device__ constexpr int record_doubles() { return 32 + kF * D; }
 // Records are stored one after the other (field offsets become immediate operands of LDS / STS instead
 // of a multiply per access) with an odd stride in doubles, so that the threads of a level, which
 // touch consecutive records, fall in different banks (ncu on the [field][block] layout it replaces:
-// 21 % of the executed instructions were IMAD address arithmetic, 40 % of the shared-memory
-// wavefronts bank conflicts).
+// 21 % of the executed instructions were IMAD address arithmetic; this layout executes 22 % fewer
+// instructions).
 template <int D>
 __host__ __device__ constexpr int record_stride() { return record_doubles<D>() | 1; }
 
