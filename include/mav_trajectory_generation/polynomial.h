@@ -1,5 +1,6 @@
 // Polynomial value type of the hot path (mirror of ref include/mav_trajectory_generation/
-// polynomial.h:34-151, 215-242; the root-finding members are out of scope).  Coefficients are
+// polynomial.h:34-242, src/polynomial.cpp:27-175; computeRoots / the *FromRoots members, which hand
+// complex roots around, are not provided).  Coefficients are
 // stored with increasing powers: c_0 + c_1 t + ... + c_{N-1} t^{N-1}.
 //
 // evaluate() runs on the GPU through the C ABI (minsnap_sample_at_host, rows a17 of SURVEY.md
@@ -11,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <utility>
 #include <vector>
 
 #include "mav_trajectory_generation/minsnap_gpu.h"
@@ -103,6 +105,79 @@ class Polynomial {
   }
 
   static inline int getConvolutionLength(int data_size, int kernel_size) { return data_size + kernel_size - 1; }
+
+  // Discrete convolution = coefficients of the product polynomial (ref src/polynomial.cpp:157-175, same
+  // summation order).  A handful of operations on caller data: computed where it is called.
+  static Eigen::VectorXd convolve(const Eigen::VectorXd& data, const Eigen::VectorXd& kernel) {
+    const int n_data = static_cast<int>(data.size()), n_kernel = static_cast<int>(kernel.size());
+    Eigen::VectorXd out(getConvolutionLength(n_data, n_kernel));
+    out.setZero();
+    for (int i = 0; i < static_cast<int>(out.size()); ++i)
+      for (int j = std::min(n_kernel - 1, i); j >= std::max(0, i - (n_data - 1)); --j) out[i] += kernel[j] * data[i - j];
+    return out;
+  }
+  Polynomial operator*(const Polynomial& rhs) const { return Polynomial(convolve(coefficients_, rhs.coefficients_)); }
+
+  // ---- extrema of one derivative over [t_start, t_end] (ref src/polynomial.cpp:57-138) --------------
+  // Candidates: t_start, t_end, then the real roots of the next derivative inside the range (ascending),
+  // isolated on the GPU (minsnap_extrema_host) instead of by Jenkins-Traub.  0 <= t_start <= t_end.
+  bool computeMinMaxCandidates(double t_start, double t_end, int derivative, std::vector<double>* candidates) const {
+    CHECK_NOTNULL(candidates);
+    candidates->clear();
+    if (N_ - derivative - 1 < 0) {
+      LOG(WARNING) << "N - derivative - 1 has to be at least 0.";
+      return false;
+    }
+    if (t_start > t_end) {
+      LOG(WARNING) << "t_start is greater than t_end.";
+      return false;
+    }
+    CHECK_GE(t_start, 0.0) << "the candidate search runs over [0, t_end]";
+    candidates->push_back(t_start);
+    candidates->push_back(t_end);
+    const int Np = minsnapSupportedN(N_) ? N_ : paddedN(N_);
+    CHECK(Np > 0) << "Polynomial::computeMinMaxCandidates: unsupported number of coefficients " << N_;
+    if (derivative > Np - 2) return true;   // the next derivative vanishes identically: no roots
+    std::vector<double> c(static_cast<size_t>(Np), 0.0);
+    for (int j = 0; j < N_; ++j) c[static_cast<size_t>(j)] = coefficients_[j];
+    const int max_roots = minsnap_extrema_max_roots(Np, derivative, 1);
+    std::vector<double> times(static_cast<size_t>(max_roots) + 2);
+    int32_t n_roots = 0;
+    gpu::check(minsnap_extrema_host(1, 1, 1, Np, c.data(), &t_end, derivative,
+                                    gpu::extremaMode(MINSNAP_EXTREMA_TRAJECTORY), 1u, nullptr, nullptr, nullptr,
+                                    nullptr, nullptr, nullptr, times.data(), nullptr, &n_roots),
+               "minsnap_extrema_host");
+    for (int i = 0; i < n_roots; ++i)
+      if (times[static_cast<size_t>(2 + i)] >= t_start) candidates->push_back(times[static_cast<size_t>(2 + i)]);
+    return true;
+  }
+
+  // Smallest and largest (signed) value of the derivative among the candidates: (time, value) pairs.
+  bool selectMinMaxFromCandidates(const std::vector<double>& candidates, int derivative,
+                                  std::pair<double, double>* minimum, std::pair<double, double>* maximum) const {
+    CHECK_NOTNULL(minimum);
+    CHECK_NOTNULL(maximum);
+    if (candidates.empty()) {
+      LOG(WARNING) << "Cannot find extrema from an empty candidates vector.";
+      return false;
+    }
+    minimum->first = maximum->first = candidates[0];
+    minimum->second = std::numeric_limits<double>::max();
+    maximum->second = std::numeric_limits<double>::lowest();
+    for (const double t : candidates) {
+      const double value = evaluate(t, derivative);
+      if (value < minimum->second) *minimum = std::make_pair(t, value);
+      if (value > maximum->second) *maximum = std::make_pair(t, value);
+    }
+    return true;
+  }
+
+  bool computeMinMax(double t_start, double t_end, int derivative, std::pair<double, double>* minimum,
+                     std::pair<double, double>* maximum) const {
+    std::vector<double> candidates;
+    if (!computeMinMaxCandidates(t_start, t_end, derivative, &candidates)) return false;
+    return selectMinMaxFromCandidates(candidates, derivative, minimum, maximum);
+  }
 
  private:
   // GPU evaluation of derivatives 0..n_deriv-1: a single-segment, single-dimension trajectory

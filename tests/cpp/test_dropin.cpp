@@ -454,6 +454,53 @@ static void testExtremaOfMagnitude(int D, int n_segments, size_t seed) {
   EXPECT_TRUE(!segments[0].computeMinMaxMagnitudeCandidateTimes(1, 0.0, 1.0, std::vector<int>{0, D}, &none));
 }
 
+// test/test_polynomial.cpp:62-128: Convolution and FindMinMax (random polynomials, extrema against sampling)
+static void testPolynomialConvolutionAndMinMax() {
+  Eigen::VectorXd coeffs_1(2), coeffs_2(2);
+  coeffs_1 << 1.0, 2.0;
+  coeffs_2 << -1.0, 3.0;
+  const Polynomial product = Polynomial(coeffs_1) * Polynomial(coeffs_2);
+  EXPECT_EQ(product.N(), 3);
+  EXPECT_TRUE(product.getCoefficients()[0] == -1.0 && product.getCoefficients()[1] == 1.0 &&
+              product.getCoefficients()[2] == 6.0);
+
+  std::srand(1234567);
+  auto uniform = [](double lo, double hi) { return lo + (hi - lo) * (std::rand() / static_cast<double>(RAND_MAX)); };
+  for (int trial = 0; trial < 40; ++trial) {
+    const int n = std::rand() % (Polynomial::kMaxN - 1) + 1;
+    Eigen::VectorXd c(n);
+    for (int i = 0; i < n; ++i) c[i] = uniform(-100.0, 100.0);
+    const Polynomial p(c);
+    const double t_start = uniform(0.0, 2.0), t_end = uniform(t_start, 4.0);
+    std::pair<double, double> lo, hi;
+    EXPECT_TRUE(p.computeMinMax(t_start, t_end, derivative_order::POSITION, &lo, &hi));
+    // sampling (ref findMinMaxBySampling), evaluated in one launch
+    std::vector<double> ts;
+    for (double t = t_start; t <= t_end; t += 1.0e-3) ts.push_back(t);
+    int n_padded = 4;                       // the batched sampler is built for N = 4, 6, ..., 12
+    while (n_padded < n) n_padded += 2;
+    Eigen::VectorXd c_padded(n_padded);
+    c_padded.setZero();
+    for (int i = 0; i < n; ++i) c_padded[i] = c[i];
+    Segment seg(n_padded, 1);
+    seg[0] = Polynomial(c_padded);
+    const std::vector<double> values = seg.evaluateBatch(ts, 1);
+    size_t i_lo = 0, i_hi = 0;
+    for (size_t i = 0; i < ts.size(); ++i) {
+      if (values[i] < values[i_lo]) i_lo = i;
+      if (values[i] > values[i_hi]) i_hi = i;
+    }
+    // the analytic extremum is at least as extreme as any sample, and close to the sampled one
+    const double scale = std::max(std::fabs(values[i_lo]), std::fabs(values[i_hi])) + 1.0;
+    EXPECT_TRUE(lo.second <= values[i_lo] + 1e-9 * scale);
+    EXPECT_TRUE(hi.second >= values[i_hi] - 1e-9 * scale);
+    // ref approxEqual on the extremum TIMES (kEqualityResolution = 1e-2); two nearly equal extrema far apart
+    // in time are told apart by value instead
+    EXPECT_TRUE(std::fabs(lo.first - ts[i_lo]) < 1.0e-2 || std::fabs(lo.second - values[i_lo]) < 1e-3 * scale);
+    EXPECT_TRUE(std::fabs(hi.first - ts[i_hi]) < 1.0e-2 || std::fabs(hi.second - values[i_hi]) < 1e-3 * scale);
+  }
+}
+
 int main() {
   struct Case {
     const char* name;
@@ -472,6 +519,7 @@ int main() {
       {"2_vertices_rand", testTwoVerticesRand},
       {"ConstraintPacking", testConstraintPacking},
       {"EvaluateRange_and_Batch", testRangeAndBatch},
+      {"Polynomial_Convolution_and_FindMinMax", testPolynomialConvolutionAndMinMax},
       {"PathOptimization_1D_segment_extrema_of_magnitude", [] { testExtremaOfMagnitude(1, 100, 1234); }},
       {"PathOptimization3D_segment_extrema_of_magnitude", [] { testExtremaOfMagnitude(3, 100, 978); }},
   };
