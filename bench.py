@@ -360,6 +360,21 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         extrema_ms = x0.elapsed_time(x1) / reps
 
+        # BASELINE configs[3]: 4,096 trajectories of 256 segments (dependency-chain bound)
+        lh_pos = torch.from_numpy(ms.random_positions_host(4096, 256, BOX_LO, BOX_HI, BASE_SEED)).cuda()
+        lh_times = ms.estimate_segment_times(lh_pos, V_MAX, A_MAX, MAGIC)
+        lh_coeffs = torch.empty((4096, 256, DIM, NCOEF), dtype=torch.float64, device="cuda")
+        for _ in range(3):
+            ms.solve_standard(lh_pos, lh_times, coeffs=lh_coeffs, want_status=False)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(20):
+            ms.solve_standard(lh_pos, lh_times, coeffs=lh_coeffs, want_status=False)
+        l1.record()
+        torch.cuda.synchronize()
+        long_horizon_ms = l0.elapsed_time(l1) / 20
+        del lh_pos, lh_times, lh_coeffs
+
         cores = os.cpu_count() or 1
         cpu_value, cpu_sample, cpu_1t = cpu_solves_per_s(pos_h, times_pin.numpy(), cores, budget_s=15.0)
         parity = parity_block(ms, torch, pos_h, times_pin.numpy(), cores)
@@ -391,6 +406,8 @@ def run_gpu_arm(args):
                       "extrema_ms": extrema_ms, "extrema_trajectories_per_s": B / (extrema_ms * 1e-3),
                       "extrema_shape": "max |velocity| of %d trajectories x %d segments "
                                        "(computeMaximumOfMagnitude)" % (B, K_SEG),
+                      "long_horizon_ms": long_horizon_ms,
+                      "long_horizon_shape": "4096 trajectories x 256 segments (configs[3]); HBM floor 0.044 ms",
                       "nccl_gather_ms": gather_ms},
         }
         emit(line)
