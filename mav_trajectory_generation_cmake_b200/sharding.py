@@ -103,6 +103,12 @@ class PeerGatherBuffer:
         block = self.rows * self.row_elems * self.itemsize
         return self._wrap(r * block, (self.rows,) + self.row_shape)
 
+    def push(self, local):
+        """Copy this rank's finished block into its slot of the peer buffer with one device-to-peer copy
+        (large NVLink writes).  Measured faster than letting the kernel store remotely and than an NCCL
+        gather: 8 GPUs 1.40 ms against 2.70 ms and 1.69 ms (profiles/r1_peer_gather.txt)."""
+        self.view().copy_(local)
+
     def whole(self):
         """All blocks, rank-major (meaningful on the owner after finish())."""
         return self._wrap(0, (self.world * self.rows,) + self.row_shape)

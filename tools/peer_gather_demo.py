@@ -52,6 +52,15 @@ def separate():
 
 
 ms_separate = timed(separate, reps=5)
+
+
+def push():
+    # local solve, then one device-to-peer copy of the block (large NVLink writes instead of per-lane stores)
+    ms.solve_standard(pos, times, coeffs=local_coeffs, want_status=False)
+    buf.push(local_coeffs)
+
+
+ms_push = timed(push, reps=5)
 # correctness: the peer buffer on rank 0 holds every rank's block, bit for bit
 ms.solve_standard(pos, times, coeffs=mine, want_status=False)
 buf.finish()
@@ -60,8 +69,9 @@ ref = gather_to_rank0(local_coeffs, world * B, dist)
 ok = True
 if rank == 0:
     ok = bool(torch.equal(buf.whole(), ref))
-    print("ranks %d: solve (local stores) %.3f ms | solve with peer stores into rank 0 %.3f ms | solve + NCCL gather %.3f ms"
-          " | peer buffer == gathered blocks: %s" % (world, ms_local, ms_fused, ms_separate, ok), flush=True)
+    print("ranks %d: solve (local stores) %.3f ms | solve with peer stores into rank 0 %.3f ms | solve + peer copy %.3f ms"
+          " | solve + NCCL gather %.3f ms | peer buffer == gathered blocks: %s"
+          % (world, ms_local, ms_fused, ms_push, ms_separate, ok), flush=True)
 buf.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
