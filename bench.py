@@ -322,6 +322,34 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gather_ms = t.item()
 
+    # the same collection through a CUDA-IPC peer buffer on rank 0: one device-to-peer copy per rank
+    peer_gather_ms = None
+    if distributed:
+        from mav_trajectory_generation_cmake_b200.sharding import PeerGatherBuffer
+        buf, ok = None, 1
+        try:
+            buf = PeerGatherBuffer(dist, B, (K_SEG, DIM, NCOEF), torch.float64, dst=0)
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        all_ok = int(flag.item()) == 1
+        if all_ok:
+            buf.push(coeffs_d[0])
+            torch.cuda.synchronize()
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            buf.push(coeffs_d[0])
+            q1.record()
+            torch.cuda.synchronize()
+            barrier()
+            t = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            peer_gather_ms = t.item()
+        if buf is not None:
+            buf.close(barrier=all_ok)
+
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
         achieved = BYTES_PER_SOLVE * B / (ms_per_step * 1e-3) / 1e9          # GB/s, this rank's kernel
@@ -408,7 +436,7 @@ def run_gpu_arm(args):
                                        "(computeMaximumOfMagnitude)" % (B, K_SEG),
                       "long_horizon_ms": long_horizon_ms,
                       "long_horizon_shape": "4096 trajectories x 256 segments (configs[3]); HBM floor 0.044 ms",
-                      "nccl_gather_ms": gather_ms},
+                      "nccl_gather_ms": gather_ms, "peer_copy_gather_ms": peer_gather_ms},
         }
         emit(line)
     if distributed:

@@ -64,14 +64,21 @@ class PeerGatherBuffer:
         self.bytes = self.world * rows_per_rank * self.row_elems * self.itemsize
         self._owner = self.rank == dst
         handle_bytes = [None]
+        self.ptr = 0
         if self._owner:
-            err, ptr = rt.cudaMalloc(self.bytes)
-            self._check(err, "cudaMalloc")
-            err, handle = rt.cudaIpcGetMemHandle(ptr)
-            self._check(err, "cudaIpcGetMemHandle")
-            handle_bytes = [bytes(handle.reserved)]
-            self.ptr = int(ptr)
+            try:
+                err, ptr = rt.cudaMalloc(self.bytes)
+                self._check(err, "cudaMalloc")
+                self.ptr = int(ptr)
+                err, handle = rt.cudaIpcGetMemHandle(ptr)
+                self._check(err, "cudaIpcGetMemHandle")
+                handle_bytes = [bytes(handle.reserved)]
+            except Exception as exc:          # every rank must still leave the broadcast below
+                handle_bytes = [None]
+                self._owner_error = exc
         dist.broadcast_object_list(handle_bytes, src=dst)
+        if handle_bytes[0] is None:
+            raise RuntimeError("PeerGatherBuffer: rank %d could not export its buffer" % dst)
         if not self._owner:
             handle = rt.cudaIpcMemHandle_t()
             handle.reserved = handle_bytes[0]
@@ -117,10 +124,13 @@ class PeerGatherBuffer:
         self._torch.cuda.synchronize()
         self._dist.barrier()
 
-    def close(self):
+    def close(self, barrier=True):
         rt = self._rt
         self._torch.cuda.synchronize()
-        self._dist.barrier()
+        if barrier:
+            self._dist.barrier()
+        if not self.ptr:
+            return
         if self._owner:
             rt.cudaFree(self.ptr)
         else:
