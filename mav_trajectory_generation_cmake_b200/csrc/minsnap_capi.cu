@@ -91,8 +91,6 @@ void retain_pool_memory() {
   cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
 }
 
-struct StreamPair {
-  cudaStream_t s[2] = {nullptr, nullptr};
   cudaError_t create() {
     for (auto& st : s) {
       cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
@@ -144,6 +142,53 @@ struct HostArena {
   }
 };
 thread_local HostArena g_arena;
+
+// Large host calls (minsnap_solve_standard_host and friends): a thread-local copy/solve/copy pipeline
+// of kDepth stages.  Each stage owns a non-blocking stream and one device block; chunk c runs
+// H2D -> kernel -> D2H on stream c % kDepth, so that H2D(c+1), the kernel of chunk c and D2H(c-1)
+// overlap on the two copy engines and the SMs, and a stage's block is reused in stream order.  The
+// streams and blocks are created on first use and kept for the life of the thread (round 1 created
+// two streams and fourteen pool allocations on every call).
+struct HostPipeline {
+  static constexpr int kDepth = 3;
+  cudaStream_t stream[kDepth] = {nullptr, nullptr, nullptr};
+  char* block[kDepth] = {nullptr, nullptr, nullptr};
+  size_t cap = 0;
+  int device = -1;
+  ~HostPipeline() { release(); }
+  void release() {
+    for (int i = 0; i < kDepth; ++i) {
+      if (block[i]) cudaFree(block[i]);
+      if (stream[i]) cudaStreamDestroy(stream[i]);
+      block[i] = nullptr;
+      stream[i] = nullptr;
+    }
+    cap = 0;
+    device = -1;
+  }
+  cudaError_t ensure(size_t bytes_per_stage) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev != device) release();
+    for (int i = 0; i < kDepth; ++i)
+      if (!stream[i] && (e = cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+    device = dev;
+    if (bytes_per_stage <= cap) return cudaSuccess;
+    for (int i = 0; i < kDepth; ++i) {
+      if (stream[i] && (e = cudaStreamSynchronize(stream[i])) != cudaSuccess) return e;
+      if (block[i]) cudaFree(block[i]);
+      block[i] = nullptr;
+    }
+    cap = 0;
+    const size_t want = align_up(bytes_per_stage, 1u << 20);
+    for (int i = 0; i < kDepth; ++i)
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&block[i]), want)) != cudaSuccess) return e;
+    cap = want;
+    return cudaSuccess;
+  }
+};
+thread_local HostPipeline g_pipeline;
 
 class SmallCall {
  public:
@@ -789,7 +834,6 @@ int minsnap_solve_standard_host(long B, int K, int D, int N, int derivative, con
       return MINSNAP_OK;
     }
   }
-  retain_pool_memory();
   const int h = N / 2;
   const int n_free = (K - 1) * (h - 1);
   // chunk = unit of the copy/solve/copy pipeline (MINSNAP_TUNE_HOST_CHUNK overrides for measurements)
@@ -799,58 +843,60 @@ int minsnap_solve_standard_host(long B, int K, int D, int N, int derivative, con
     if (want >= 16) chunk_pref = want;
   }
   const long chunk = std::min<long>(B, chunk_pref);
-  StreamPair sp;
-  CU(sp.create());
+  // Stage layout: one device block per pipeline stage, carved into the per-chunk arrays.
+  const size_t nc = (size_t)chunk;
+  size_t off = 0;
+  auto carve = [&off](size_t bytes) { const size_t at = off; off += align_up(bytes ? bytes : 16, 256); return at; };
+  const size_t o_pos = carve(sizeof(double) * nc * (K + 1) * D);
+  const size_t o_end = carve(h_end_derivatives ? sizeof(double) * nc * 2 * (h - 1) * D : 0);
+  const size_t o_tm = carve(sizeof(double) * nc * K);
+  const size_t o_co = carve(sizeof(double) * nc * K * D * N);
+  const size_t o_fr = carve(h_free_values ? sizeof(double) * nc * (n_free > 0 ? n_free : 1) * D : 0);
+  const size_t o_cs = carve(h_cost ? sizeof(double) * nc : 0);
+  const size_t o_ss = carve(h_status ? sizeof(int32_t) * nc : 0);
+  CU(g_pipeline.ensure(off));
   int rc = MINSNAP_OK;
   {
-    Scratch pos[2], end[2], tm[2], co[2], fr[2], cs[2], ss[2];
-    const size_t nc = (size_t)chunk;
-    int which = 0;
-    for (int s = 0; s < 2; ++s) {
-      TRY(pos[s].alloc(sizeof(double) * nc * (K + 1) * D, sp.s[s]));
-      TRY(end[s].alloc(sizeof(double) * nc * 2 * (h - 1) * D, sp.s[s]));
-      TRY(tm[s].alloc(sizeof(double) * nc * K, sp.s[s]));
-      TRY(co[s].alloc(sizeof(double) * nc * K * D * N, sp.s[s]));
-      TRY(fr[s].alloc(sizeof(double) * nc * (n_free > 0 ? n_free : 1) * D, sp.s[s]));
-      TRY(cs[s].alloc(sizeof(double) * nc, sp.s[s]));
-      TRY(ss[s].alloc(sizeof(int32_t) * nc, sp.s[s]));
-    }
-    for (long b0 = 0; b0 < B; b0 += chunk, which ^= 1) {
+    int stage = 0;
+    for (long b0 = 0; b0 < B; b0 += chunk, stage = (stage + 1) % HostPipeline::kDepth) {
       const long nb = std::min(chunk, B - b0);
-      cudaStream_t st = sp.s[which];
-      TRY(cudaMemcpyAsync(pos[which].ptr, h_positions + (size_t)b0 * (K + 1) * D,
-                          sizeof(double) * nb * (K + 1) * D, cudaMemcpyHostToDevice, st));
+      cudaStream_t st = g_pipeline.stream[stage];
+      char* base = g_pipeline.block[stage];
+      double* d_pos = reinterpret_cast<double*>(base + o_pos);
+      double* d_end = reinterpret_cast<double*>(base + o_end);
+      double* d_tm = reinterpret_cast<double*>(base + o_tm);
+      double* d_co = reinterpret_cast<double*>(base + o_co);
+      double* d_fr = reinterpret_cast<double*>(base + o_fr);
+      double* d_cs = reinterpret_cast<double*>(base + o_cs);
+      int32_t* d_ss = reinterpret_cast<int32_t*>(base + o_ss);
+      TRY(cudaMemcpyAsync(d_pos, h_positions + (size_t)b0 * (K + 1) * D, sizeof(double) * nb * (K + 1) * D,
+                          cudaMemcpyHostToDevice, st));
       if (h_end_derivatives)
-        TRY(cudaMemcpyAsync(end[which].ptr, h_end_derivatives + (size_t)b0 * 2 * (h - 1) * D,
+        TRY(cudaMemcpyAsync(d_end, h_end_derivatives + (size_t)b0 * 2 * (h - 1) * D,
                             sizeof(double) * nb * 2 * (h - 1) * D, cudaMemcpyHostToDevice, st));
       if (h_times)
-        TRY(cudaMemcpyAsync(tm[which].ptr, h_times + (size_t)b0 * K, sizeof(double) * nb * K,
-                            cudaMemcpyHostToDevice, st));
-      rc = minsnap_solve_standard(nb, K, D, N, derivative, pos[which].as<double>(),
-                                  h_end_derivatives ? end[which].as<double>() : nullptr,
-                                  h_times ? tm[which].as<double>() : nullptr, v_max, a_max, magic,
-                                  (!h_times && h_times_out) ? tm[which].as<double>() : nullptr,
-                                  co[which].as<double>(), h_free_values ? fr[which].as<double>() : nullptr,
-                                  h_cost ? cs[which].as<double>() : nullptr,
-                                  h_status ? ss[which].as<int32_t>() : nullptr, st);
+        TRY(cudaMemcpyAsync(d_tm, h_times + (size_t)b0 * K, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
+      rc = minsnap_solve_standard(nb, K, D, N, derivative, d_pos, h_end_derivatives ? d_end : nullptr,
+                                  h_times ? d_tm : nullptr, v_max, a_max, magic,
+                                  (!h_times && h_times_out) ? d_tm : nullptr, d_co, h_free_values ? d_fr : nullptr,
+                                  h_cost ? d_cs : nullptr, h_status ? d_ss : nullptr, st);
       if (rc != MINSNAP_OK) goto done;
-      TRY(cudaMemcpyAsync(h_coeffs + (size_t)b0 * K * D * N, co[which].ptr, sizeof(double) * nb * K * D * N,
+      TRY(cudaMemcpyAsync(h_coeffs + (size_t)b0 * K * D * N, d_co, sizeof(double) * nb * K * D * N,
                           cudaMemcpyDeviceToHost, st));
       if (h_times_out) {
         if (h_times) std::memcpy(h_times_out + (size_t)b0 * K, h_times + (size_t)b0 * K, sizeof(double) * nb * K);
-        else TRY(cudaMemcpyAsync(h_times_out + (size_t)b0 * K, tm[which].ptr, sizeof(double) * nb * K,
+        else TRY(cudaMemcpyAsync(h_times_out + (size_t)b0 * K, d_tm, sizeof(double) * nb * K,
                                  cudaMemcpyDeviceToHost, st));
       }
       if (h_free_values && n_free > 0)
-        TRY(cudaMemcpyAsync(h_free_values + (size_t)b0 * n_free * D, fr[which].ptr,
-                            sizeof(double) * nb * n_free * D, cudaMemcpyDeviceToHost, st));
-      if (h_cost) TRY(cudaMemcpyAsync(h_cost + b0, cs[which].ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
-      if (h_status)
-        TRY(cudaMemcpyAsync(h_status + b0, ss[which].ptr, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(h_free_values + (size_t)b0 * n_free * D, d_fr, sizeof(double) * nb * n_free * D,
+                            cudaMemcpyDeviceToHost, st));
+      if (h_cost) TRY(cudaMemcpyAsync(h_cost + b0, d_cs, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+      if (h_status) TRY(cudaMemcpyAsync(h_status + b0, d_ss, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
     }
   done:;
   }
-  for (auto st : sp.s) {
+  for (auto st : g_pipeline.stream) {
     cudaError_t es = cudaStreamSynchronize(st);
     if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
   }
