@@ -91,20 +91,6 @@ void retain_pool_memory() {
   cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
 }
 
-  cudaError_t create() {
-    for (auto& st : s) {
-      cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-      if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
-  }
-  ~StreamPair() {
-    for (auto st : s)
-      if (st) cudaStreamDestroy(st);
-  }
-};
-
-
 // ---------------------------------------------------------------------------------------
 // Small host calls (one trajectory from the C++ drop-in classes): a thread-local staging arena
 // -- one pinned host block and one device block of equal size, grown on demand, released when
