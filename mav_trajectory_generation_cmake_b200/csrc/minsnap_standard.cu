@@ -13,7 +13,7 @@
 
 #include "minsnap_standard_fast.cuh"
 #include "minsnap_standard_bcr.cuh"
-#include "minsnap_standard_ws.cuh"
+#include "minsnap_standard_tm.cuh"
 
 namespace minsnap {
 
@@ -99,19 +99,21 @@ bool standard_supported(int K, int D, int N, int derivative) {
          (N == 10 && derivative == 4 && D >= 1 && D <= 3 && K > fast::kMaxK && bcr::supported(K, D));
 }
 
-// Kernel choice for the fast route: the two-lane kernel (default) or the warp-specialised CTA
-// (MINSNAP_STANDARD_KERNEL=ws; correct, parity-tested, but measured slower on B200: its matrix
-// warp and dimension warps idle on each other and the per-warp overheads triple).
-static bool use_ws_kernel(int K, int D, int N, int derivative) {
-  if (!ws::supported(K, D, N, derivative)) return false;
+// Kernel choice for the fast route with coefficients: the second-generation kernel (block storage in
+// tensor memory, coefficients out through the TMA; minsnap_standard_tm.cuh) where it applies -- even K
+// up to 12 and a 16-byte aligned coefficient array -- else the first-generation two-lane kernel.
+// MINSNAP_STANDARD_KERNEL=pair forces the first generation (A/B measurements).
+static bool use_tm_kernel(const fast::FastParams& p, int D, int N, int derivative) {
+  if (!tm::supported(p.K, D, N, derivative) || p.sweep_S > 0 || !p.coeffs) return false;
+  if (reinterpret_cast<uintptr_t>(p.coeffs) % 16 != 0) return false;
   const char* v = std::getenv("MINSNAP_STANDARD_KERNEL");
-  return v && std::strcmp(v, "ws") == 0;
+  return !(v && std::strcmp(v, "pair") == 0);
 }
 
-static cudaError_t launch_fast_route(const fast::FastParams& p, int D, bool coeffs, bool ws_kernel, cudaStream_t stream) {
-#define MINSNAP_FAST_CASE(D_)                                                                         \
-  case D_:                                                                                            \
-    if (ws_kernel) return coeffs ? ws::launch_d<D_, true>(p, stream) : ws::launch_d<D_, false>(p, stream); \
+static cudaError_t launch_fast_route(const fast::FastParams& p, int D, bool coeffs, bool tm_kernel, cudaStream_t stream) {
+  if (coeffs && tm_kernel) return tm::launch(p, D, stream);
+#define MINSNAP_FAST_CASE(D_) \
+  case D_:                    \
     return coeffs ? fast::launch_d<D_, true>(p, stream) : fast::launch_d<D_, false>(p, stream);
   switch (D) {
     MINSNAP_FAST_CASE(1)
@@ -196,7 +198,7 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
       if (cost) return launch_cost(a.B, a.K, a.D, a.N, a.derivative, a.d_coeffs, t, cost, stream);
       return cudaSuccess;
     }
-    return launch_fast_route(p, a.D, true, use_ws_kernel(a.K, a.D, a.N, a.derivative), stream);
+    return launch_fast_route(p, a.D, true, use_tm_kernel(p, a.D, a.N, a.derivative), stream);
   }
   return generic_route(a.B, 1, a.K, a.D, a.N, a.derivative, a.d_positions, a.d_end_derivatives, times, a.d_coeffs,
                        a.d_free_out, a.d_cost, a.d_status, stream);
@@ -210,7 +212,7 @@ cudaError_t launch_cost_sweep(const SweepArgs& a, cudaStream_t stream) {
     p.times = a.d_times; p.v_max = 0; p.a_max = 0; p.magic = 0; p.times_out = nullptr;
     p.coeffs = nullptr; p.free_out = nullptr; p.cost = a.d_cost; p.status = a.d_status; p.sweep_S = a.S;
     p.aligned16 = reinterpret_cast<uintptr_t>(a.d_times) % 16 == 0;
-    return launch_fast_route(p, a.D, false, use_ws_kernel(a.K, a.D, a.N, a.derivative), stream);
+    return launch_fast_route(p, a.D, false, false, stream);
   }
   return generic_route(a.B, a.S, a.K, a.D, a.N, a.derivative, a.d_positions, a.d_end_derivatives, a.d_times, nullptr,
                        nullptr, a.d_cost, a.d_status, stream);

@@ -611,20 +611,61 @@ def test_solve_standard_other_dimensions(ms, oracle, torch_cuda, D):
     assert (np.abs(out["free_values"].cpu().numpy() - want) / scale).max() <= 1e-8
 
 
-def test_warp_specialised_variant_parity(ms, oracle, torch_cuda, monkeypatch):
-    """The opt-in warp-specialised kernel solves the same problems to the same tolerance."""
+@pytest.mark.parametrize("K", [2, 4, 6, 8, 10])
+@pytest.mark.parametrize("D", [1, 2, 3])
+def test_two_kernel_generations_agree(ms, oracle, torch_cuda, monkeypatch, K, D):
+    """The second-generation kernel (tensor-memory block storage, TMA copy-out: even K <= 10) against the
+    first-generation thread-pair kernel on the same inputs, with non-zero end derivatives, cost, status,
+    free derivatives, a ragged batch, and times computed on the device."""
     torch = torch_cuda
-    K, B = 10, 200
-    pos, times = random_batch(oracle, B, K, seed=321)
-    monkeypatch.setenv("MINSNAP_STANDARD_KERNEL", "ws")
-    out = ms.solve_standard(dev(torch, pos), dev(torch, times), want_cost=True, want_free=True)
-    torch.cuda.synchronize()
+    B = 16 * 9 + 5
+    rng = np.random.default_rng(4242 + 10 * K + D)
+    # random walks whose steps are at least 1 in every dimension: consecutive vertices stay apart also for D = 1
+    steps = rng.uniform(1.0, 4.0, size=(B, K + 1, D)) * rng.choice([-1.0, 1.0], size=(B, K + 1, D))
+    pos = np.cumsum(steps, axis=1)
+    end = rng.uniform(-1.0, 1.0, size=(B, 2, 4, D))
+    pos_d, end_d = dev(torch, pos), dev(torch, end)
+    results = {}
+    for name in ("tm", "pair"):
+        if name == "pair":
+            monkeypatch.setenv("MINSNAP_STANDARD_KERNEL", "pair")
+        results[name] = ms.solve_standard(pos_d, None, end_derivatives=end_d, v_max=3.0, a_max=5.0, want_cost=True,
+                                          want_free=True, want_times=True)
+        torch.cuda.synchronize()
     monkeypatch.delenv("MINSNAP_STANDARD_KERNEL")
-    pair = ms.solve_standard(dev(torch, pos), dev(torch, times), want_cost=True, want_free=True)
-    ref = oracle_solve_batch(oracle, standard_mask(K), batch_values(pos), times)
-    assert coeff_rel_err(out["coeffs"].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
-    assert coeff_rel_err(out["coeffs"].cpu().numpy(), pair["coeffs"].cpu().numpy()) <= 1e-9
-    assert np.abs(out["cost"].cpu().numpy() / ref["cost"] - 1.0).max() <= COST_TOL
+    a, b = results["tm"], results["pair"]
+    assert int((a["status"] != 0).sum()) == 0 and int((b["status"] != 0).sum()) == 0
+    assert np.array_equal(a["times"].cpu().numpy(), b["times"].cpu().numpy())
+    assert coeff_rel_err(a["coeffs"].cpu().numpy(), b["coeffs"].cpu().numpy()) <= 1e-12
+    fa, fb = a["free_values"].cpu().numpy(), b["free_values"].cpu().numpy()
+    if fb.size:
+        assert np.abs(fa - fb).max() <= 1e-12 * max(1.0, np.abs(fb).max())
+    assert np.abs(a["cost"].cpu().numpy() / b["cost"].cpu().numpy() - 1.0).max() <= 1e-12
+    # and against the oracle (reference-order arithmetic) on a few problems
+    t = a["times"].cpu().numpy()
+    mask = standard_mask(K)
+    for i in (0, B // 2, B - 1):
+        vals = np.zeros((K + 1, 5, D))
+        vals[:, 0, :] = pos[i]
+        vals[0, 1:, :] = end[i, 0]
+        vals[K, 1:, :] = end[i, 1]
+        ref = oracle.solve(10, K, D, 4, mask, vals, t[i])
+        assert coeff_rel_err(a["coeffs"][i].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
+
+
+def test_second_generation_status_bits(ms, torch_cuda):
+    """A non-positive segment time is flagged by the recovery phase of the second-generation kernel."""
+    torch = torch_cuda
+    K, B = 10, 40
+    rng = np.random.default_rng(77)
+    pos = np.cumsum(rng.uniform(1.0, 4.0, size=(B, K + 1, 3)), axis=1)
+    times = rng.uniform(1.0, 3.0, size=(B, K))
+    times[7, 3] = -1.0
+    times[33, 9] = 0.0
+    out = ms.solve_standard(dev(torch, pos), dev(torch, times))
+    st = out["status"].cpu().numpy()
+    assert st[7] & 2 and st[33] & 2
+    assert int((st[np.setdiff1d(np.arange(B), [7, 33])] != 0).sum()) == 0
 
 
 def test_randomised_shapes_fast_route_vs_general_route(ms, torch_cuda):
