@@ -111,7 +111,10 @@ static bool use_tm_kernel(const fast::FastParams& p, int D, int N, int derivativ
 }
 
 static cudaError_t launch_fast_route(const fast::FastParams& p, int D, bool coeffs, bool tm_kernel, cudaStream_t stream) {
-  if (coeffs && tm_kernel) return tm::launch(p, D, stream);
+  if (coeffs && tm_kernel) {
+    const cudaError_t e = tm::launch(p, D, stream);
+    if (e != cudaErrorNotSupported) return e;   // no tensor map: the first-generation kernel takes over
+  }
 #define MINSNAP_FAST_CASE(D_) \
   case D_:                    \
     return coeffs ? fast::launch_d<D_, true>(p, stream) : fast::launch_d<D_, false>(p, stream);

@@ -1,33 +1,35 @@
-// Standard-mask solve, second generation (N = 10, snap, even K <= 10): the thread-pair
-// elimination of minsnap_standard_fast.cuh with the two costs ncu attributed to it removed --
-// the per-lane coefficient stores (every lane of a store instruction in its own 128-byte line)
-// and the lane-serial coefficient recovery behind them.
+// Standard-mask solve, second generation (N = 10, snap, even K <= 12): the thread-pair
+// elimination of minsnap_standard_fast.cuh with the cost ncu attributed to its output removed --
+// per-lane coefficient stores, every lane of a store instruction in its own 128-byte line.
 //
-//  * Solve phase (a thread PAIR per trajectory, 16 trajectories per warp): unchanged algebra --
-//    lane 2q eliminates top-down, lane 2q+1 bottom-up, they meet at the middle block.  The Z (4x4)
-//    of every eliminated block is lane-private scratch, written once in the forward sweep and read
-//    once in the back substitution: it now lives in TENSOR MEMORY (tcgen05.st / tcgen05.ld, shape
-//    32x32b: thread i of a warp owns TMEM lane 32 (warp % 4) + i, a block is 32 consecutive 32-bit
-//    columns).  No MMA is involved: TMEM is used as what it physically is, a 128-lane x 512-column
-//    register-file extension next to the SM, and it frees the shared memory the next phase needs.
-//    w -> x of every interior vertex goes to shared memory as X[trajectory][vertex][derivative][dim]
-//    in actual orientation.
-//  * Recovery phase (a thread per SEGMENT, in output order): task t = 32 i + lane of a warp is
-//    segment t mod K of trajectory t / K, so the 32 tasks of an iteration produce 32 x 80 D
-//    CONTIGUOUS bytes of the coefficient array.  Each lane evaluates c = A^-1 d for its segment
-//    one dimension at a time (10 live coefficients), parks them in a shared-memory tile, and one
-//    elected lane hands the whole tile to the TMA (cp.async.bulk.global.shared::cta, SASS UBLKCP):
-//    5 bulk copies of 7,680 bytes per 16 trajectories instead of 640 store instructions.  The
-//    9-term dot products of 32 independent segments run at FP64 throughput, not at the latency of
-//    one lane's dependency chain.
+//  * Block storage in TENSOR MEMORY.  The Z (4x4) and w (4xD) of every eliminated block are
+//    lane-private scratch, written once in the forward sweep and read once in the back
+//    substitution.  They live in TMEM (tcgen05.st / tcgen05.ld, shape 32x32b: thread i of a warp
+//    owns TMEM lane 32 (warp % 4) + i, a block is 32 + 8 D consecutive 32-bit columns).  No MMA is
+//    involved: TMEM is used as what it physically is, a 128-lane x 512-column register-file
+//    extension next to the SM, and the 21.5 KB of shared memory per warp it replaces hold the
+//    copy-out tiles instead.
+//  * Coefficients leave through the TMA as TENSOR stores.  Lanes 0..15 of a warp are the top-down
+//    lanes of 16 consecutive trajectories, lanes 16..31 the bottom-up lanes.  After back-substitution
+//    step j the top-down lanes hold segment j of their trajectories and the bottom-up lanes segment
+//    K-1-j: 16 pieces of 80 D bytes each, 2400 D... apart in the coefficient array [B][K][10 D] -- a
+//    {10 D, 1, 16} box of that 3-D tensor.  Every lane recovers its segment one dimension at a time
+//    (10 live coefficients), parks it in its row of a dense shared-memory tile, and ONE elected lane
+//    issues two cp.async.bulk.tensor.3d stores per step (SASS UTMASTG); rows past the end of a ragged
+//    batch are clipped by the tensor map.  Two tiles per side: a step never waits for the previous copy.
+//  * Recovery is interleaved with the back substitution (segment j is recovered as soon as x_j is
+//    known), so x never leaves the registers and the 15 independent dot-product chains of a
+//    dimension fill the FP64 pipe while the next block's TMEM loads are in flight.
 //
-// Control flow is uniform across the warp (even K: both lanes of a pair eliminate the same
-// number of blocks), which the warp-collective tcgen05.ld/st require.  Other shapes (odd K,
-// K = 1, K > 10, the cost sweep, unaligned outputs) keep the first-generation kernel.
+// Control flow is uniform across the warp (even K: both lanes of a pair eliminate the same number
+// of blocks), which the warp-collective tcgen05.ld/st require.  Other shapes (odd K, K = 1,
+// K > 12, the cost sweep, unaligned outputs) keep the first-generation kernel.
 //
 // Arithmetic is that of minsnap_standard_fast.cuh (same closed-form blocks, same 2x2-Schur inverse,
 // same summation orders).
 #pragma once
+#include <cuda.h>
+
 #include "minsnap_standard_fast.cuh"
 
 namespace minsnap {
@@ -41,7 +43,7 @@ using fast::TimePowers;
 using fast::tri;
 
 constexpr int kWarpsPerCta = 4;   // one warp per TMEM lane quarter
-constexpr int kMaxK = 10;
+constexpr int kMaxK = 12;
 
 #define H1T(r, s) (minsnap_tables::kH1_N10_d4[(r) * 10 + (s)])
 #define A1T(i, r) (minsnap_tables::kA1inv_N10[(i) * 10 + (r)])
@@ -57,7 +59,22 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// one 4x4 block = 16 doubles = 32 columns of the calling thread's TMEM lane
+__device__ __forceinline__ void tmem_store(uint32_t taddr, const double (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "r"(taddr), "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])), "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])) : "memory");
+}
+__device__ __forceinline__ void tmem_load(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_store(uint32_t taddr, const double (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               :: "r"(taddr), "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])), "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])), "r"(__double2loint(v[4])), "r"(__double2hiint(v[4])), "r"(__double2loint(v[5])), "r"(__double2hiint(v[5])), "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(__double2loint(v[7])), "r"(__double2hiint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_load(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_store(uint32_t taddr, const double (&v)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
                :: "r"(taddr), "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])), "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])), "r"(__double2loint(v[4])), "r"(__double2hiint(v[4])), "r"(__double2loint(v[5])), "r"(__double2hiint(v[5])), "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(__double2loint(v[7])), "r"(__double2hiint(v[7])), "r"(__double2loint(v[8])), "r"(__double2hiint(v[8])), "r"(__double2loint(v[9])), "r"(__double2hiint(v[9])), "r"(__double2loint(v[10])), "r"(__double2hiint(v[10])), "r"(__double2loint(v[11])), "r"(__double2hiint(v[11])), "r"(__double2loint(v[12])), "r"(__double2hiint(v[12])), "r"(__double2loint(v[13])), "r"(__double2hiint(v[13])), "r"(__double2loint(v[14])), "r"(__double2hiint(v[14])), "r"(__double2loint(v[15])), "r"(__double2hiint(v[15])) : "memory");
@@ -69,48 +86,113 @@ __device__ __forceinline__ void tmem_load(uint32_t taddr, uint32_t (&r)[32]) {
 
 __device__ __forceinline__ double pair_to_double(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
 
-// ---- bulk copy shared -> global (TMA, non-tensor form) --------------------------------------
-__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uint32_t bytes) {
+// A block is stored / loaded in pieces of 4 doubles (x8): an operand group of 8 consecutive registers
+// is what the values' natural allocation provides (measured: the x32 / x16 forms cost 56 register
+// moves per block on either side).
+template <int D>
+__device__ __forceinline__ void tmem_store_block(uint32_t taddr, const double (&Z)[kF][kF], const double (&w)[kF][D]) {
+#pragma unroll
+  for (int a = 0; a < kF; ++a) {
+    const double v[4] = {Z[a][0], Z[a][1], Z[a][2], Z[a][3]};
+    tmem_store(taddr + 8 * a, v);
+  }
+  double flat[kF * D + 3];
+#pragma unroll
+  for (int e = 0; e < kF * D; ++e) flat[e] = w[e / D][e % D];
+#pragma unroll
+  for (int e = kF * D; e < kF * D + 3; ++e) flat[e] = 0.0;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {   // 4 D doubles = D pieces
+    const double v[4] = {flat[4 * c], flat[4 * c + 1], flat[4 * c + 2], flat[4 * c + 3]};
+    tmem_store(taddr + 32 + 8 * c, v);
+  }
+}
+
+// Z and w of one stored block: issue the loads, wait, unpack.
+template <int D>
+__device__ __forceinline__ void tmem_load_block(uint32_t taddr, double (&Z)[kF][kF], double (&w)[kF][D]) {
+  uint32_t z[kF][8], r[D][8];
+#pragma unroll
+  for (int a = 0; a < kF; ++a) tmem_load(taddr + 8 * a, z[a]);
+#pragma unroll
+  for (int c = 0; c < D; ++c) tmem_load(taddr + 32 + 8 * c, r[c]);
+  tmem_wait_ld();
+#pragma unroll
+  for (int a = 0; a < kF; ++a)
+#pragma unroll
+    for (int b2 = 0; b2 < kF; ++b2) Z[a][b2] = pair_to_double(z[a][2 * b2], z[a][2 * b2 + 1]);
+#pragma unroll
+  for (int e = 0; e < kF * D; ++e) w[e / D][e % D] = pair_to_double(r[e / 4][2 * (e % 4)], r[e / 4][2 * (e % 4) + 1]);
+}
+
+// ---- TMA: tensor store shared -> global ----------------------------------------------------
+__device__ __forceinline__ void tensor_store_3d(const CUtensorMap* map, const double* ssrc, int c0, int c1, int c2) {
   const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(s), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const double* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __host__ __device__ inline int stored_blocks(int K) {
   const int mA = (K - 1) / 2;
   return mA > 0 ? mA - 1 : 0;
 }
+template <int D>
+__host__ __device__ constexpr int block_columns() { return 32 + 8 * D; }
+template <int D>
 inline int tmem_columns(int K) {
-  const int need = stored_blocks(K) * 32;
+  const int need = stored_blocks(K) * block_columns<D>();
   int cols = 32;
   while (cols < need) cols <<= 1;
   return cols;
 }
-// per-warp shared memory, in doubles: positions [16][(K+1) D], times [16][K], X [4 D][16 K + 1], the
-// copy-out tile [32][10 D], 16 status words.
-// X is element-major: entry e = (derivative, dimension) of the vertex that STARTS segment t = traj K + seg of
-// the batch sits at X[e][t]; the vertex that ends it at X[e][t + 1].  Column traj K (vertex 0 of a trajectory,
-// which is also the end vertex K of the trajectory before it) holds the end derivatives when they are zero,
-// i.e. zeros that are written once.  Consecutive lanes of the recovery phase read consecutive words.
+// per-warp shared memory, in doubles, every region a multiple of 128 bytes (the TMA reads the tiles):
+// positions [16][(K+1) D], times [16][K], copy-out tiles [2 buffers][2 sides][16][10 D]
 template <int D>
 struct WarpSmem {
-  size_t pos, tim, x, x_pitch, tile, flags, total;
+  size_t pos, tim, tile, total;
   __host__ __device__ explicit WarpSmem(int K) {
     size_t o = 0;
-    pos = o; o += ((size_t)kPairsPerWarp * (K + 1) * D + 1) & ~(size_t)1;
-    tim = o; o += ((size_t)kPairsPerWarp * K + 1) & ~(size_t)1;
-    x_pitch = (size_t)kPairsPerWarp * K + 1;
-    x = o; o += ((size_t)kF * D * x_pitch + 1) & ~(size_t)1;
-    tile = o; o += (size_t)32 * D * kN;
-    flags = o; o += 8;
+    pos = o; o += ((size_t)kPairsPerWarp * (K + 1) * D + 15) & ~(size_t)15;
+    tim = o; o += ((size_t)kPairsPerWarp * K + 15) & ~(size_t)15;
+    tile = o; o += (size_t)2 * 2 * kPairsPerWarp * D * kN;   // 16 x 80 D bytes is a multiple of 128
     total = o;
   }
 };
 
-template <int D, bool kCost, bool kBoundary>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel(FastParams p, int tmem_cols) {
+// ref estimateSegmentTimes (src/vertex.cpp:162-178), same expression as minsnap_estimate_segment_times.  Out of
+// line: inlined, its loop-invariant division was hoisted to the top of the kernel and ran on every launch.
+template <int D>
+__device__ __noinline__ void estimate_times(int K, double v_max, double a_max, double magic, double* times_out,
+                                            const double* pos_s, double* time_s, long base, int n_here, int lane) {
+  const int per_pos = (K + 1) * D;
+  for (int e = lane; e < n_here * K; e += kWarp) {
+    const int r = e / K, o = e - r * K;
+    const double* p0 = pos_s + r * per_pos + o * D;
+    double s2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double diff = p0[D + d] - p0[d];
+      s2 += diff * diff;
+    }
+    const double distance = sqrt(s2);
+    const double T = distance / v_max * 2 * (1.0 + magic * v_max / a_max * exp(-distance / v_max * 2));
+    time_s[r * K + o] = T;
+    if (times_out) times_out[(base + r) * K + o] = T;
+  }
+}
+
+template <int D, bool kCost, bool kExtras>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const __grid_constant__ CUtensorMap coeff_map) {
   extern __shared__ __align__(128) double smem[];
   __shared__ uint32_t tmem_base_slot;
   const int lane = threadIdx.x & 31;
@@ -120,6 +202,35 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
   constexpr int kVec = kF * D;    // doubles per vertex vector
   constexpr int kTile = D * kN;   // doubles per segment
 
+  const WarpSmem<D> lay(K);
+  double* wbase = smem + (size_t)warp * lay.total;
+  double* pos_s = wbase + lay.pos;     // [16][per_pos]
+  double* time_s = wbase + lay.tim;    // [16][K]
+  double* tile_s = wbase + lay.tile;   // [2][2][16][kTile]
+
+  const long pairs_per_cta = (long)kWarpsPerCta * kPairsPerWarp;
+  const long stride = (long)gridDim.x * pairs_per_cta;
+  long base = (long)blockIdx.x * pairs_per_cta + (long)warp * kPairsPerWarp;
+  // inputs by cp.async: every chunk of a batch in flight before the single wait
+  auto issue_inputs = [&](long b0) {
+    const int n = (int)min((long)kPairsPerWarp, p.B - b0);
+    fast::async_copy_doubles(pos_s, p.positions + b0 * per_pos, n * per_pos, lane, p.aligned16);
+    if (p.times) fast::async_copy_doubles(time_s, p.times + b0 * K, n * K, lane, p.aligned16);
+    __pipeline_commit();
+  };
+  // The first batch's loads are in flight while the CTA allocates its tensor memory; the batch that will
+  // take this warp's place on the SM one wave from now is pulled into L2 (TMA prefetch), so that only the
+  // first wave of a launch waits for DRAM.
+  if (base < p.B) issue_inputs(base);
+  if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&coeff_map)) : "memory");
+  if (lane == 0 && p.aligned16) {
+    const long pf = base + (long)resident_warps * kPairsPerWarp;
+    if (pf + kPairsPerWarp <= p.B) {
+      bulk_prefetch_l2(p.positions + pf * per_pos, (uint32_t)(kPairsPerWarp * per_pos * sizeof(double)));
+      if (p.times) bulk_prefetch_l2(p.times + pf * K, (uint32_t)(kPairsPerWarp * K * sizeof(double)));
+    }
+  }
+
   // tensor memory: one allocation per CTA, every warp works in its own lane quarter
   if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)tmem_cols);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -128,81 +239,46 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t taddr = tmem_base + ((uint32_t)(warp & 3) << 21);   // lane field (bits 31..16) = 32 (warp % 4)
 
-  const WarpSmem<D> lay(K);
-  double* wbase = smem + (size_t)warp * lay.total;
-  double* pos_s = wbase + lay.pos;      // [16][per_pos]
-  double* time_s = wbase + lay.tim;     // [16][K]; a segment's entry is replaced by its cost term once recovered
-  double* x_s = wbase + lay.x;          // [kVec][16 K + 1]: w of stored blocks, then x of every interior vertex
-  double* tile_s = wbase + lay.tile;    // [32][kTile]
-  int* flags_s = reinterpret_cast<int*>(wbase + lay.flags);   // [16] status bits found by the recovery phase
-  const int x_pitch = (int)lay.x_pitch;
-
-  const int side = lane & 1;   // 0: top-down lane, 1: bottom-up lane
-  const int q = lane >> 1;     // pair index within the warp
-  const int nb = K - 1;        // unknown blocks (odd)
-  const int mA = nb / 2;       // blocks eliminated by either lane; the middle block is vertex mA + 1
+  const int side = lane >> 4;   // 0: top-down lane, 1: bottom-up lane
+  const int q = lane & 15;      // trajectory of the batch
+  const int nb = K - 1;         // unknown blocks (odd)
+  const int mA = nb / 2;        // blocks eliminated by either lane; the middle block is vertex mA + 1
   const double flip[kF] = {side ? -1.0 : 1.0, 1.0, side ? -1.0 : 1.0, 1.0};   // (-1)^k, k = 1..4, bottom-up lane
-  const unsigned inv_k = 65536u / (unsigned)K + 1u;   // t / K == (t * inv_k) >> 16 for t < 16 K (K <= 16)
-  // the boundary columns of X (vertex 0 of every trajectory, and the one past the last) stay zero
-  for (int e = lane; e < kVec * (kPairsPerWarp + 1); e += kWarp) x_s[(e / (kPairsPerWarp + 1)) * x_pitch + (e % (kPairsPerWarp + 1)) * K] = 0.0;
 
-  const long pairs_per_cta = (long)kWarpsPerCta * kPairsPerWarp;
-  const long stride = (long)gridDim.x * pairs_per_cta;
-  for (long base = (long)blockIdx.x * pairs_per_cta + (long)warp * kPairsPerWarp; base < p.B; base += stride) {
+  int buf = 0;
+  for (; base < p.B; base += stride) {
     const int n_here = (int)min((long)kPairsPerWarp, p.B - base);
     const long prob = base + q;
     const bool active = q < n_here;
-    // ---- inputs: cp.async, every chunk in flight before the single wait ------------------------
-    __syncwarp();   // the previous batch's readers are done with the inputs
-    fast::async_copy_doubles(pos_s, p.positions + base * per_pos, n_here * per_pos, lane, p.aligned16);
-    if (p.times) fast::async_copy_doubles(time_s, p.times + base * K, n_here * K, lane, p.aligned16);
-    __pipeline_commit();
-    if (lane < kPairsPerWarp) flags_s[lane] = 0;
     __pipeline_wait_prior(0);
     __syncwarp();
     if (!p.times) {
-      // ref estimateSegmentTimes (src/vertex.cpp:162-178), same expression as minsnap_estimate_segment_times
-      for (int e = lane; e < n_here * K; e += kWarp) {
-        const int r = e / K, o = e - r * K;
-        const double* p0 = pos_s + r * per_pos + o * D;
-        double s2 = 0.0;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const double diff = p0[D + d] - p0[d];
-          s2 += diff * diff;
-        }
-        const double distance = sqrt(s2);
-        const double T = distance / p.v_max * 2 * (1.0 + p.magic * p.v_max / p.a_max * exp(-distance / p.v_max * 2));
-        time_s[r * K + o] = T;
-        if (p.times_out) p.times_out[(base + r) * K + o] = T;
-      }
+      estimate_times<D>(K, p.v_max, p.a_max, p.magic, p.times_out, pos_s, time_s, base, n_here, lane);
       __syncwarp();
     }
-    // idle pairs of a ragged last batch run on the first pair's inputs (nothing of theirs is stored)
+    // idle pairs of a ragged last batch run on the first pair's inputs (nothing of theirs reaches memory)
     const int qi = active ? q : 0;
     const double* my_pos = pos_s + qi * per_pos;
     const double* my_time = time_s + qi * K;
-    double* my_x = x_s + q * K;   // column of vertex v of this trajectory: my_x[v], entry e at + e x_pitch
     // local chain: vertex j <-> actual vertex (side ? K - j : j); segment j <-> actual (side ? K-1-j : j)
     auto local_T = [&](int j) { return my_time[side ? K - 1 - j : j]; };
     auto local_p = [&](int j, int d) { return my_pos[(side ? K - j : j) * D + d]; };
-    auto x_slot = [&](int j) { return my_x + (side ? K - j : j); };   // local vertex j (1 <= j <= K-1)
 
     int status = 0;
     const double* bd_src = nullptr;   // boundary derivatives of the lane's end of the chain (actual coordinates)
-    if (kBoundary && p.end_derivatives && active) bd_src = p.end_derivatives + (prob * 2 + side) * kVec;
-    auto bd = [&](int a, int d) { return bd_src ? flip[a] * bd_src[a * D + d] : 0.0; };
+    if (kExtras && p.end_derivatives && active) bd_src = p.end_derivatives + (prob * 2 + side) * kVec;
+    auto bd = [&](int a, int d) { return (kExtras && bd_src) ? flip[a] * bd_src[a * D + d] : 0.0; };
 
+    double xm[kF][D];             // middle block solution, local coordinates; then the far vector of each step
+    double Z[kF][kF], w[kF][D];   // after the forward sweep: the lane's LAST block (never leaves the registers)
+#pragma unroll
+    for (int a = 0; a < kF; ++a) {
+#pragma unroll
+      for (int b = 0; b < kF; ++b) Z[a][b] = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) w[a][d] = 0.0;
+    }
     {
-      double xm[kF][D];             // middle block solution, local coordinates
-      double Z[kF][kF], w[kF][D];   // after the forward sweep: the lane's LAST block (never leaves the registers)
-#pragma unroll
-      for (int a = 0; a < kF; ++a) {
-#pragma unroll
-        for (int b = 0; b < kF; ++b) Z[a][b] = 0.0;
-#pragma unroll
-        for (int d = 0; d < D; ++d) w[a][d] = 0.0;
-      }
       auto rhs_block = [&](const TimePowers& tprev, const TimePowers& tnext, const double (&dprev)[D],
                            const double (&dnext)[D], double (&out)[kF][D]) {
 #pragma unroll
@@ -226,7 +302,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
       }
       fast::diag_block(tp_prev, tp_next, S);
       rhs_block(tp_prev, tp_next, dp_prev, dp_next, g);
-      if (bd_src) {
+      if (kExtras && bd_src) {
         double E0[kF][kF];
         fast::coupling_block(tp_prev, E0);
 #pragma unroll
@@ -268,17 +344,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
           for (int a = 0; a < kF; ++a) w[a][d] = col[a];
         }
         if (more) {
-          // Z of block j goes to tensor memory, w to the vertex's slot of X (x replaces it later)
-          {
-            const double zv[16] = {Z[0][0], Z[0][1], Z[0][2], Z[0][3], Z[1][0], Z[1][1], Z[1][2], Z[1][3],
-                                   Z[2][0], Z[2][1], Z[2][2], Z[2][3], Z[3][0], Z[3][1], Z[3][2], Z[3][3]};
-            tmem_store(taddr + (uint32_t)((j - 1) * 32), zv);
-          }
-          double* ws = x_slot(j);
-#pragma unroll
-          for (int a = 0; a < kF; ++a)
-#pragma unroll
-            for (int d = 0; d < D; ++d) ws[(a * D + d) * x_pitch] = w[a][d];
+          // block j goes to tensor memory: Z at column (j-1) pitch, w right behind it
+          tmem_store_block<D>(taddr + (uint32_t)((j - 1) * block_columns<D>()), Z, w);
           // advance to block j+1: D_{j+1} - E^T Z,  b_{j+1} - E^T w
           tp_prev = tp_next;
           tp_next = tp_new;
@@ -356,7 +423,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
         }
         fast::diag_block(ta, tb, Sm);
         rhs_block(ta, tb, da, db, gm);
-        if (kBoundary && p.end_derivatives && active && K == 2) {
+        if (kExtras && p.end_derivatives && active && K == 2) {
           // both boundary couplings reach the middle block directly
           const double* src = p.end_derivatives + (prob * 2 + 0) * kVec;
           double E0[kF][kF];
@@ -382,7 +449,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
         // subtract the top-down contribution first, then the bottom-up one, on both lanes
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
-          const double other = __shfl_xor_sync(0xffffffffu, C[i], 1);
+          const double other = __shfl_xor_sync(0xffffffffu, C[i], 16);
           const double cA = side ? other : C[i];
           const double cB = side ? C[i] : other;
           Sm[i] = (Sm[i] - cA) - cB;
@@ -391,49 +458,51 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
         for (int a = 0; a < kF; ++a)
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            const double other = __shfl_xor_sync(0xffffffffu, c[a][d], 1);
+            const double other = __shfl_xor_sync(0xffffffffu, c[a][d], 16);
             const double cA = side ? other : c[a][d];
             const double cB = side ? c[a][d] : other;
             gm[a][d] = (gm[a][d] - cA) - cB;
           }
         double Si[10];
         if (!fast::spd4_inverse(Sm, Si)) status |= 1;
-        double* ms_ = my_x + (mA + 1);   // the middle vertex mA + 1, actual coordinates = the top-down lane's
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           const double in[4] = {gm[0][d], gm[1][d], gm[2][d], gm[3][d]};
           double col[4];
           fast::sym4_apply(Si, in, col);
 #pragma unroll
-          for (int a = 0; a < kF; ++a) {
-            xm[a][d] = flip[a] * col[a];   // -> local coordinates
-            if (side == 0) ms_[(a * D + d) * x_pitch] = col[a];
-          }
+          for (int a = 0; a < kF; ++a) xm[a][d] = flip[a] * col[a];   // -> local coordinates
         }
       }
-      if (p.free_out && active && side == 0) {
+      if (kExtras && p.free_out && active && side == 0) {
         double* dst = p.free_out + (prob * (long)nb + mA) * kVec;
 #pragma unroll
         for (int a = 0; a < kF; ++a)
 #pragma unroll
           for (int d = 0; d < D; ++d) dst[a * D + d] = xm[a][d];
       }
+    }
 
-      // ---- back substitution outwards: x_j = w_j - Z_j x_{j+1}, stored over w_j in actual orientation ----
-      for (int j = mA; j >= 1; --j) {
-        double* xs = x_slot(j);
-        if (j < mA) {
-          uint32_t z[32];
-          tmem_load(taddr + (uint32_t)((j - 1) * 32), z);
-#pragma unroll
-          for (int a = 0; a < kF; ++a)
-#pragma unroll
-            for (int d = 0; d < D; ++d) w[a][d] = xs[(a * D + d) * x_pitch];
-          tmem_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) Z[e / 4][e % 4] = pair_to_double(z[2 * e], z[2 * e + 1]);
-        }
-        double x_near[kF][D];
+    // ---- back substitution outwards, each step followed by the recovery of its segment --------
+    // Step j (mA .. 0) produces x of local vertex j (x_j = w_j - Z_j x_{j+1}; the boundary values at
+    // j = 0) and recovers local segment j, which lies between local vertices j (near) and j + 1 (far).
+    double cost_acc = 0.0;
+    int nonfinite = 0;
+    int pending_j = -1;
+    auto flush_tile = [&](int jj, int b) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const double* t0 = tile_s + (size_t)(b * 2) * kPairsPerWarp * kTile;
+        tensor_store_3d(&coeff_map, t0, 0, jj, (int)base);
+        tensor_store_3d(&coeff_map, t0 + kPairsPerWarp * kTile, 0, K - 1 - jj, (int)base);
+        bulk_commit();
+      }
+    };
+    for (int j = mA; j >= 0; --j) {
+      double x_near[kF][D];
+      if (j >= 1) {
+        if (j < mA) tmem_load_block<D>(taddr + (uint32_t)((j - 1) * block_columns<D>()), Z, w);
 #pragma unroll
         for (int a = 0; a < kF; ++a)
 #pragma unroll
@@ -443,14 +512,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
             for (int b = 0; b < kF; ++b) acc = fma(-Z[a][b], xm[b][d], acc);
             x_near[a][d] = acc;
           }
-#pragma unroll
-        for (int a = 0; a < kF; ++a)
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            xm[a][d] = x_near[a][d];   // becomes the far vector of the next step
-            xs[(a * D + d) * x_pitch] = flip[a] * x_near[a][d];
-          }
-        if (p.free_out && active) {
+        if (kExtras && p.free_out && active) {
           const int v = side ? K - j : j;   // actual vertex
           double* dst = p.free_out + (prob * (long)nb + (v - 1)) * kVec;
 #pragma unroll
@@ -458,52 +520,52 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
 #pragma unroll
             for (int d = 0; d < D; ++d) dst[a * D + d] = flip[a] * x_near[a][d];
         }
+      } else {
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) x_near[a][d] = bd(a, d);
       }
-    }
-    status |= __shfl_xor_sync(0xffffffffu, status, 1);
-    __syncwarp();   // X is complete
 
-    // ---- recovery (ref updateSegmentsFromCompactConstraints, LIN.i:252-273): one thread per segment, in
-    //      output order; task t = 32 it + lane is segment t mod K of trajectory t / K of this batch ----
-    const int n_tasks = n_here * K;
-    for (int it = 0; it * 32 < kPairsPerWarp * K; ++it) {
-      const int t = it * 32 + lane;
-      const int traj = (int)(((unsigned)t * inv_k) >> 16);
-      const int seg = t - traj * K;
-      const bool valid = t < n_tasks;
-      const double T = time_s[t];
-      const double* tp = pos_s + (t + traj) * D;   // positions of vertices seg, seg + 1 of trajectory traj
-      const double* xp = x_s + t;                   // start vertex at xp[e x_pitch], end vertex one word further
-      int flags = (T > 0.0) ? 0 : 2;   // MINSNAP_STATUS_BAD_TIME
+      if (pending_j >= 0) {
+        // The tile of the previous step leaves now: its 16 top-down rows are segment j+1 of 16 consecutive
+        // trajectories, its 16 bottom-up rows segment K-2-j -- two {10 D, 1, 16} boxes of the coefficient
+        // tensor [B][K][10 D].  Issued here, one back-substitution later, the proxy fence finds the tile's
+        // stores long complete.
+        flush_tile(pending_j, buf ^ 1);
+      }
+      // recovery of local segment j (ref updateSegmentsFromCompactConstraints, LIN.i:252-273) in ACTUAL
+      // orientation: the bottom-up lane's segment starts at its far vertex; odd derivatives change sign.
+      const int seg = side ? K - 1 - j : j;
+      const double T = my_time[seg];
+      if (!(T > 0.0)) status |= 2;   // MINSNAP_STATUS_BAD_TIME; the two lanes cover all K segments
       const double T2 = T * T, T3 = T2 * T, T4 = T2 * T2;
-      const double tk[kF] = {T, T2, T3, T4};
+      const double tks[kF] = {flip[0] * T, T2, flip[2] * T3, T4};   // the sign of the lane's coordinates folded into T^k
+      const double kas[kF] = {flip[0] * A1T(1, 1), A1T(2, 2), flip[2] * A1T(3, 3), A1T(4, 4)};
       const double i1 = fast::fast_rcp(T);
       const double i2 = i1 * i1, i4 = i2 * i2, i5 = i4 * i1;
       const double ipow[5] = {i5, i5 * i1, i5 * i2, i4 * i4, i4 * i5};   // T^-5 .. T^-9
+      double* tile = tile_s + ((size_t)(buf * 2 + side) * kPairsPerWarp + q) * kTile;
       double u[2 * kF + 1][D];   // [dp, T^k start_k (k = 1..4), T^k end_k (k = 1..4)]
       double cf[D][kN];
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        const double p0 = tp[d];
-        u[0][d] = tp[D + d] - p0;
+        const double p0 = my_pos[seg * D + d];
+        u[0][d] = my_pos[(seg + 1) * D + d] - p0;
         cf[d][0] = p0;
       }
 #pragma unroll
       for (int a = 0; a < kF; ++a)
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          double s_val = xp[(a * D + d) * x_pitch];
-          double e_val = xp[(a * D + d) * x_pitch + 1];
-          if (kBoundary && p.end_derivatives && valid) {
-            // end derivatives given by the caller (global memory): the boundary columns of X hold zeros
-            if (seg == 0) s_val = p.end_derivatives[((base + traj) * 2 + 0) * kVec + a * D + d];
-            if (seg == K - 1) e_val = p.end_derivatives[((base + traj) * 2 + 1) * kVec + a * D + d];
-          }
-          u[1 + a][d] = tk[a] * s_val;
-          u[1 + kF + a][d] = tk[a] * e_val;
-          cf[d][1 + a] = A1T(1 + a, 1 + a) * s_val;
+          const double s_val = side ? xm[a][d] : x_near[a][d];   // local coordinates; the signs are in tks / kas
+          const double e_val = side ? x_near[a][d] : xm[a][d];
+          u[1 + a][d] = tks[a] * s_val;
+          u[1 + kF + a][d] = tks[a] * e_val;
+          cf[d][1 + a] = kas[a] * s_val;
         }
-      // row-outer, dimension-inner: every table constant is fetched once per segment, not once per dimension
+      // row-outer, dimension-inner: every table constant is fetched once per segment and is live only while it
+      // is applied to the D dimensions (no uniform-register hoarding)
 #pragma unroll
       for (int i = 5; i < kN; ++i) {
         double acc[D];
@@ -523,17 +585,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         const int e9 = __double2hiint(cf[d][kN - 1]) & 0x7ff00000, e4 = __double2hiint(cf[d][kF]) & 0x7ff00000;
-        if (e9 == 0x7ff00000 || e4 == 0x7ff00000) flags |= 4;
+        if (e9 == 0x7ff00000 || e4 == 0x7ff00000) nonfinite = 1;
       }
-      // the tile is free once the previous bulk copy has read it
-      if (lane == 0) bulk_wait_read_all();
+      // the copies that read this buffer two steps ago are done with it
+      if (lane == 0) bulk_wait_read<1>();
       __syncwarp();
-      double2* t2 = reinterpret_cast<double2*>(tile_s + lane * kTile);
+      {
+        double2* t2 = reinterpret_cast<double2*>(tile);
 #pragma unroll
-      for (int e = 0; e < kTile; e += 2) t2[e / 2] = make_double2(cf[e / kN][e % kN], cf[(e + 1) / kN][(e + 1) % kN]);
+        for (int e = 0; e < kTile; e += 2) t2[e / 2] = make_double2(cf[e / kN][e % kN], cf[(e + 1) / kN][(e + 1) % kN]);
+      }
+      double qsum = 0.0;
       if (kCost) {
         // u^T Hred1 u * T^-7: the per-segment quadratic form in scaled variables
-        double qsum = 0.0;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           double qd = 0.0;
@@ -550,28 +614,30 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) solve_standard_tm_kernel
           }
           qsum += qd;
         }
-        time_s[t] = qsum * (i5 * i2);   // only this task read the entry
       }
-      if (flags && valid) atomicOr(flags_s + traj, flags);
-      // the 32 segments of this iteration are 32 x 80 D contiguous bytes of the coefficient array
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        const int n_valid = min(32, n_tasks - it * 32);
-        if (n_valid > 0)
-          bulk_store(p.coeffs + (base * K + (long)it * 32) * kTile, tile_s, (uint32_t)(n_valid * kTile * sizeof(double)));
-        bulk_commit();
-      }
+      if (kCost) cost_acc = fma(qsum, i5 * i2, cost_acc);
+      pending_j = j;   // this step's tile leaves during the next step (or after the loop)
+      buf ^= 1;
+#pragma unroll
+      for (int a = 0; a < kF; ++a)
+#pragma unroll
+        for (int d = 0; d < D; ++d) xm[a][d] = x_near[a][d];
     }
-    __syncwarp();
-    if (kCost && p.cost && lane < n_here) {
-      double acc = 0.0;
-      for (int s = 0; s < K; ++s) acc += time_s[lane * K + s];
-      p.cost[base + lane] = 0.5 * acc;
+
+    flush_tile(pending_j, buf ^ 1);   // the last step's tile
+    if (kCost && p.cost) {
+      cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, 16);
+      if (active && side == 0) p.cost[prob] = 0.5 * cost_acc;
     }
-    if (p.status && active && side == 0) p.status[prob] = status | flags_s[q];
+    if (nonfinite) status |= 4;
+    status |= __shfl_xor_sync(0xffffffffu, status, 16);
+    if (p.status && active && side == 0) p.status[prob] = status;
+    if (base + stride < p.B) {
+      __syncwarp();   // every lane is done with this batch's inputs
+      issue_inputs(base + stride);
+    }
   }
-  if (lane == 0) bulk_wait_read_all();   // shared memory stays valid until the last copy has read it
+  if (lane == 0) bulk_wait_read<0>();   // shared memory stays valid until the last copies have read it
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
@@ -584,14 +650,46 @@ inline bool supported(int K, int D, int N, int derivative) {
   return N == 10 && derivative == 4 && D >= 1 && D <= 3 && K >= 2 && K <= kMaxK && (K % 2) == 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// The coefficient array as a 3-D tensor [B][K][10 D] of doubles with a {10 D, 1, 16} box.
+inline bool make_coeff_map(CUtensorMap* map, double* coeffs, long B, int K, int D) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn || B > 0x7fffffffL) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)(D * kN), (cuuint64_t)K, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)(D * kN) * sizeof(double), (cuuint64_t)K * D * kN * sizeof(double)};
+  const cuuint32_t box[3] = {(cuuint32_t)(D * kN), 1u, (cuuint32_t)kPairsPerWarp};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, coeffs, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// cudaErrorNotSupported: no tensor map could be made; the caller takes the first-generation kernel.
 template <int D>
 inline cudaError_t launch_d(FastParams p, cudaStream_t stream) {
   const size_t smem = WarpSmem<D>(p.K).total * sizeof(double) * kWarpsPerCta;
-  if (smem > kMaxDynamicSmem) return cudaErrorInvalidConfiguration;
-  const int cols = tmem_columns(p.K);
-  void (*kernel)(FastParams, int) =
-      p.end_derivatives ? (p.cost ? solve_standard_tm_kernel<D, true, true> : solve_standard_tm_kernel<D, false, true>)
-                        : (p.cost ? solve_standard_tm_kernel<D, true, false> : solve_standard_tm_kernel<D, false, false>);
+  if (smem > kMaxDynamicSmem) return cudaErrorNotSupported;
+  CUtensorMap map;
+  if (!make_coeff_map(&map, p.coeffs, p.B, p.K, D)) return cudaErrorNotSupported;
+  const int cols = tmem_columns<D>(p.K);
+  const bool extras = p.end_derivatives || p.free_out;
+  void (*kernel)(FastParams, int, int, const CUtensorMap) =
+      extras ? (p.cost ? solve_standard_tm_kernel<D, true, true> : solve_standard_tm_kernel<D, false, true>)
+             : (p.cost ? solve_standard_tm_kernel<D, true, false> : solve_standard_tm_kernel<D, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long per_cta = (long)kWarpsPerCta * kPairsPerWarp;
@@ -600,7 +698,11 @@ inline cudaError_t launch_d(FastParams p, cudaStream_t stream) {
   // balances the SMs); very large batches loop
   const long max_grid = 148L * 64;
   if (grid > max_grid) grid = max_grid;
-  kernel<<<(int)grid, kWarpsPerCta * 32, smem, stream>>>(p, cols);
+  int dev = 0, sms = 148, ctas = 2;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, kWarpsPerCta * 32, smem) != cudaSuccess || ctas < 1) ctas = 2;
+  if (ctas > 512 / cols) ctas = 512 / cols;   // tensor memory: 512 columns per SM
+  kernel<<<(int)grid, kWarpsPerCta * 32, smem, stream>>>(p, cols, sms * ctas * kWarpsPerCta, map);
   return cudaGetLastError();
 }
 
