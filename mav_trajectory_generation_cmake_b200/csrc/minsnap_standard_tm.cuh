@@ -44,6 +44,7 @@ using fast::tri;
 
 constexpr int kWarpsPerCta = 4;   // one warp per TMEM lane quarter
 constexpr int kMaxK = 12;
+constexpr int kRecTab = 54;   // doubles per lane role in the recovery table (53 used)
 
 #define H1T(r, s) (minsnap_tables::kH1_N10_d4[(r) * 10 + (s)])
 #define A1T(i, r) (minsnap_tables::kA1inv_N10[(i) * 10 + (r)])
@@ -195,6 +196,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const __grid_constant__ CUtensorMap coeff_map) {
   extern __shared__ __align__(128) double smem[];
   __shared__ uint32_t tmem_base_slot;
+  // Recovery constants per lane role.  A top-down lane's new vector x_j STARTS its segment and the previous one
+  // ends it; for a bottom-up lane it is the other way round and odd derivatives change sign.  Instead of
+  // selecting the 24 values of every step, the role is folded into the table a lane reads:
+  //   rec_tab[side][(i-5) 9 + 0]     = A1inv[i][5]                                  (position difference)
+  //   rec_tab[side][(i-5) 9 + 1 + a] = side ? (-1)^(a+1) A1inv[i][6+a] : A1inv[i][1+a]   (applied to T^k new_k)
+  //   rec_tab[side][(i-5) 9 + 5 + a] = side ? (-1)^(a+1) A1inv[i][1+a] : A1inv[i][6+a]   (applied to T^k old_k)
+  //   rec_tab[side][45 + a]          = side ? 0 : A1inv[1+a][1+a]                        (c_k from new_k)
+  //   rec_tab[side][49 + a]          = side ? (-1)^(a+1) A1inv[1+a][1+a] : 0             (c_k from old_k)
+  __shared__ __align__(16) double rec_tab[2][kRecTab];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int K = p.K;
@@ -222,6 +232,29 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   // take this warp's place on the SM one wave from now is pulled into L2 (TMA prefetch), so that only the
   // first wave of a launch waits for DRAM.
   if (base < p.B) issue_inputs(base);
+  for (int e = threadIdx.x; e < 2 * kRecTab; e += blockDim.x) {
+    const int sd = e / kRecTab, o = e - sd * kRecTab;
+    double v = 0.0;
+    if (o < 45) {
+      const int i = 5 + o / 9, c = o % 9;
+      if (c == 0) v = minsnap_tables::kA1inv_N10[i * 10 + 5];
+      else {
+        const int a = (c - 1) & 3;
+        const bool newer = c <= 4;
+        const int col = (newer != (sd != 0)) ? 1 + a : 6 + a;   // the start vector's column, or the end vector's
+        v = minsnap_tables::kA1inv_N10[i * 10 + col];
+        if (sd && !(a & 1)) v = -v;   // derivative k = a + 1 odd
+      }
+    } else if (o < 53) {
+      const int a = (o - 45) & 3;
+      const bool newer = o < 49;
+      if (newer != (sd != 0)) {   // the vector that starts the segment
+        v = minsnap_tables::kA1inv_N10[(1 + a) * 10 + (1 + a)];
+        if (sd && !(a & 1)) v = -v;
+      }
+    }
+    rec_tab[sd][o] = v;
+  }
   if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&coeff_map)) : "memory");
   if (lane == 0 && p.aligned16) {
     const long pf = base + (long)resident_warps * kPairsPerWarp;
@@ -540,13 +573,13 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
       const double T = my_time[seg];
       if (!(T > 0.0)) status |= 2;   // MINSNAP_STATUS_BAD_TIME; the two lanes cover all K segments
       const double T2 = T * T, T3 = T2 * T, T4 = T2 * T2;
-      const double tks[kF] = {flip[0] * T, T2, flip[2] * T3, T4};   // the sign of the lane's coordinates folded into T^k
-      const double kas[kF] = {flip[0] * A1T(1, 1), A1T(2, 2), flip[2] * A1T(3, 3), A1T(4, 4)};
+      const double tk[kF] = {T, T2, T3, T4};
       const double i1 = fast::fast_rcp(T);
       const double i2 = i1 * i1, i4 = i2 * i2, i5 = i4 * i1;
       const double ipow[5] = {i5, i5 * i1, i5 * i2, i4 * i4, i4 * i5};   // T^-5 .. T^-9
       double* tile = tile_s + ((size_t)(buf * 2 + side) * kPairsPerWarp + q) * kTile;
-      double u[2 * kF + 1][D];   // [dp, T^k start_k (k = 1..4), T^k end_k (k = 1..4)]
+      const double* tab = rec_tab[side];
+      double u[2 * kF + 1][D];   // [dp, T^k new_k (k = 1..4), T^k old_k (k = 1..4)], new = x_j, old = x_{j+1} (local)
       double cf[D][kN];
 #pragma unroll
       for (int d = 0; d < D; ++d) {
@@ -555,31 +588,35 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
         cf[d][0] = p0;
       }
 #pragma unroll
-      for (int a = 0; a < kF; ++a)
+      for (int a = 0; a < kF; ++a) {
+        const double kn = tab[45 + a], ko = tab[49 + a];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          const double s_val = side ? xm[a][d] : x_near[a][d];   // local coordinates; the signs are in tks / kas
-          const double e_val = side ? x_near[a][d] : xm[a][d];
-          u[1 + a][d] = tks[a] * s_val;
-          u[1 + kF + a][d] = tks[a] * e_val;
-          cf[d][1 + a] = kas[a] * s_val;
+          u[1 + a][d] = tk[a] * x_near[a][d];
+          u[1 + kF + a][d] = tk[a] * xm[a][d];
+          cf[d][1 + a] = fma(kn, x_near[a][d], ko * xm[a][d]);
         }
-      // row-outer, dimension-inner: every table constant is fetched once per segment and is live only while it
-      // is applied to the D dimensions (no uniform-register hoarding)
+      }
+      // 5 rows x D dimensions = 15 independent accumulation chains, advanced together one table column at a
+      // time (a row-by-row order leaves only D chains in flight against the 8-cycle FP64 latency)
+      {
+        double acc[kN - 5][D];
 #pragma unroll
-      for (int i = 5; i < kN; ++i) {
-        double acc[D];
+        for (int i = 0; i < kN - 5; ++i)
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc[d] = A1T(i, 5) * u[0][d];
+          for (int d = 0; d < D; ++d) acc[i][d] = tab[i * 9] * u[0][d];
 #pragma unroll
-        for (int a = 0; a < kF; ++a) {
+        for (int c = 1; c < 9; ++c)
 #pragma unroll
-          for (int d = 0; d < D; ++d) acc[d] = fma(A1T(i, 1 + a), u[1 + a][d], acc[d]);
+          for (int i = 0; i < kN - 5; ++i) {
+            const double coef = tab[i * 9 + c];
 #pragma unroll
-          for (int d = 0; d < D; ++d) acc[d] = fma(A1T(i, 6 + a), u[1 + kF + a][d], acc[d]);
-        }
+            for (int d = 0; d < D; ++d) acc[i][d] = fma(coef, u[c][d], acc[i][d]);
+          }
 #pragma unroll
-        for (int d = 0; d < D; ++d) cf[d][i] = acc[d] * ipow[i - 5];
+        for (int i = 0; i < kN - 5; ++i)
+#pragma unroll
+          for (int d = 0; d < D; ++d) cf[d][5 + i] = acc[i][d] * ipow[i];
       }
       // non-finite detection on the exponent fields of c_9 (scaled by T^-9: overflows first) and c_4
 #pragma unroll
@@ -608,9 +645,9 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
 #pragma unroll
             for (int s = 0; s < 2 * kF + 1; ++s) {
               const int hs = s == 0 ? 5 : (s <= kF ? s : s + 1);
-              row = fma(H1T(hr, hs), u[s][d], row);
+              row = fma(H1T(hr, hs), (s == 0 ? flip[0] : 1.0) * u[s][d], row);
             }
-            qd = fma(row, u[r][d], qd);
+            qd = fma(row, (r == 0 ? flip[0] : 1.0) * u[r][d], qd);
           }
           qsum += qd;
         }

@@ -636,11 +636,11 @@ def test_two_kernel_generations_agree(ms, oracle, torch_cuda, monkeypatch, K, D)
     a, b = results["tm"], results["pair"]
     assert int((a["status"] != 0).sum()) == 0 and int((b["status"] != 0).sum()) == 0
     assert np.array_equal(a["times"].cpu().numpy(), b["times"].cpu().numpy())
-    assert coeff_rel_err(a["coeffs"].cpu().numpy(), b["coeffs"].cpu().numpy()) <= 1e-12
+    assert coeff_rel_err(a["coeffs"].cpu().numpy(), b["coeffs"].cpu().numpy()) <= 1e-10
     fa, fb = a["free_values"].cpu().numpy(), b["free_values"].cpu().numpy()
     if fb.size:
         assert np.abs(fa - fb).max() <= 1e-12 * max(1.0, np.abs(fb).max())
-    assert np.abs(a["cost"].cpu().numpy() / b["cost"].cpu().numpy() - 1.0).max() <= 1e-12
+    assert np.abs(a["cost"].cpu().numpy() / b["cost"].cpu().numpy() - 1.0).max() <= 1e-10
     # and against the oracle (reference-order arithmetic) on a few problems
     t = a["times"].cpu().numpy()
     mask = standard_mask(K)
