@@ -330,3 +330,138 @@ class ReferenceRpoly:
             return None
         keep = [z.real for z in r if abs(z.imag) <= np.finfo(np.float64).eps and t0 <= z.real <= t1]
         return np.array(sorted(keep))
+
+
+class ReferenceCore:
+    """The reference's own value classes (oracle/_ref/libmav_ref_core.so, built by oracle/Makefile from
+    /root/reference/.../src/{vertex,polynomial,segment,trajectory,motion_defines,rpoly}.cpp against the
+    Eigen / glog stand-ins of oracle/ref_shim/).  TEST USE ONLY: pins the oracle to the reference itself."""
+
+    PATH = os.path.join(_HERE, "_ref", "libmav_ref_core.so")
+
+    @classmethod
+    def available(cls):
+        if not os.path.exists(cls.PATH) and os.path.exists("/root/reference/mav_trajectory_generation/src/vertex.cpp"):
+            subprocess.call(["make", "-C", _HERE, "-s", "ref"])
+        return os.path.exists(cls.PATH)
+
+    def __init__(self):
+        assert self.available()
+        self.lib = C.CDLL(self.PATH)
+        self.lib.refc_polynomial_evaluate.restype = C.c_double
+        self.lib.refc_trajectory_max_time.restype = C.c_double
+
+    @staticmethod
+    def _d(a):
+        return np.ascontiguousarray(np.asarray(a, np.float64))
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def create_random_positions(self, max_derivative, K, pos_min, pos_max, seed):
+        lo, hi = self._d(pos_min), self._d(pos_max)
+        D = lo.shape[0]
+        pos = np.zeros((K + 1, D))
+        nc = np.zeros(K + 1, np.int32)
+        rc = self.lib.refc_create_random_positions(max_derivative, K, D, self._p(lo), self._p(hi), C.c_uint64(seed),
+                                                   self._p(pos), self._p(nc))
+        assert rc == 0
+        return pos, nc
+
+    def estimate_segment_times(self, positions, v_max, a_max, magic=6.5):
+        pos = self._d(positions)
+        K, D = pos.shape[0] - 1, pos.shape[1]
+        t = np.zeros(K)
+        n = self.lib.refc_estimate_segment_times(K, D, self._p(pos), C.c_double(v_max), C.c_double(a_max),
+                                                 C.c_double(magic), self._p(t))
+        assert n == K
+        return t
+
+    def base_coefficients(self, n):
+        out = np.zeros((n, n))
+        self.lib.refc_base_coefficients(n, self._p(out))
+        return out
+
+    def base_coeffs_with_time(self, N, derivative, t):
+        out = np.zeros(N)
+        self.lib.refc_base_coeffs_with_time(N, derivative, C.c_double(t), self._p(out))
+        return out
+
+    def polynomial_evaluate(self, c, t, derivative):
+        c = self._d(c)
+        return self.lib.refc_polynomial_evaluate(len(c), self._p(c), C.c_double(t), derivative)
+
+    def polynomial_evaluate_all(self, c, t, n_deriv):
+        c = self._d(c)
+        out = np.zeros(n_deriv)
+        self.lib.refc_polynomial_evaluate_all(len(c), self._p(c), C.c_double(t), n_deriv, self._p(out))
+        return out
+
+    def polynomial_get_coefficients(self, c, derivative):
+        c = self._d(c)
+        out = np.zeros(len(c))
+        self.lib.refc_polynomial_get_coefficients(len(c), self._p(c), derivative, self._p(out))
+        return out
+
+    def convolve(self, a, b):
+        a, b = self._d(a), self._d(b)
+        out = np.zeros(len(a) + len(b))
+        n = self.lib.refc_convolve(self._p(a), len(a), self._p(b), len(b), self._p(out))
+        return out[:n].copy()
+
+    def polynomial_min_max(self, c, t_start, t_end, derivative):
+        c = self._d(c)
+        out = np.zeros(4)
+        ok = self.lib.refc_polynomial_min_max(len(c), self._p(c), C.c_double(t_start), C.c_double(t_end), derivative,
+                                              self._p(out))
+        return bool(ok), (out[0], out[1]), (out[2], out[3])
+
+    def segment_evaluate(self, seg_coeffs, T, t, derivative):
+        c = self._d(seg_coeffs)
+        D, N = c.shape
+        out = np.zeros(D)
+        self.lib.refc_segment_evaluate(N, D, self._p(c), C.c_double(T), C.c_double(t), derivative, self._p(out))
+        return out
+
+    def trajectory_evaluate(self, coeffs, times, t, derivative):
+        c, tm = self._d(coeffs), self._d(times)
+        K, D, N = c.shape
+        out = np.zeros(D)
+        self.lib.refc_trajectory_evaluate(N, K, D, self._p(c), self._p(tm), C.c_double(t), derivative, self._p(out))
+        return out
+
+    def trajectory_max_time(self, coeffs, times):
+        c, tm = self._d(coeffs), self._d(times)
+        K, D, N = c.shape
+        return self.lib.refc_trajectory_max_time(N, K, D, self._p(c), self._p(tm))
+
+    def trajectory_evaluate_range(self, coeffs, times, t_start, t_end, dt, derivative, max_out=1 << 20):
+        c, tm = self._d(coeffs), self._d(times)
+        K, D, N = c.shape
+        out = np.zeros((max_out, D))
+        ts = np.zeros(max_out)
+        n = self.lib.refc_trajectory_evaluate_range(N, K, D, self._p(c), self._p(tm), C.c_double(t_start), C.c_double(t_end),
+                                                    C.c_double(dt), derivative, max_out, self._p(out), self._p(ts))
+        n = min(n, max_out)
+        return out[:n].copy(), ts[:n].copy()
+
+    def segment_minmax_candidates(self, seg_coeffs, T, derivative, t_start, t_end, dims=None):
+        c = self._d(seg_coeffs)
+        D, N = c.shape
+        d = np.ascontiguousarray(np.arange(D) if dims is None else np.asarray(dims), dtype=np.int32)
+        ct, cv = np.zeros(4 * N), np.zeros(4 * N)
+        n = self.lib.refc_segment_minmax_candidates(N, D, self._p(c), C.c_double(T), derivative, C.c_double(t_start),
+                                                    C.c_double(t_end), self._p(d), len(d), 4 * N, self._p(ct), self._p(cv))
+        if n < 0:
+            return None
+        return ct[:n].copy(), cv[:n].copy()
+
+    def trajectory_minmax_magnitude(self, coeffs, times, derivative, dims=None):
+        c, tm = self._d(coeffs), self._d(times)
+        K, D, N = c.shape
+        d = np.ascontiguousarray(np.arange(D) if dims is None else np.asarray(dims), dtype=np.int32)
+        out = np.zeros(6)
+        ok = self.lib.refc_trajectory_minmax_magnitude(N, K, D, self._p(c), self._p(tm), derivative, self._p(d), len(d),
+                                                       self._p(out))
+        return bool(ok), (out[0], out[1], int(out[2])), (out[3], out[4], int(out[5]))
