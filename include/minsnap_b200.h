@@ -234,6 +234,33 @@ MINSNAP_API int minsnap_time_gradient(long B, int K, int D, int N, int derivativ
                                       double increment, double w_d, double w_t, double* d_gradient,
                                       double* d_segment_cost, minsnap_stream_t stream);
 
+/* ---- collision cost of solved trajectories against a signed-distance grid ------
+ * ref: PolynomialOptimizationNonLinear::getCostAndGradientCollision (NL.i:1523-1709, cost and collision flag),
+ *      getCostAndGradientPotentialESDF (NL.i:1713-1806), getDistanceSDF (NL.i:1843-1905), getCostPotential
+ *      (NL.i:2319-2345), triLerp (NL.i:2451-2464).
+ * The trajectory is walked at the fixed time increment `dt` (coll_check_time_increment; t advances by repeated
+ * addition, segment by segment); a sample is charged once the path length since the last charged sample reaches
+ * `map_resolution`, with  potential(position) * |velocity| * (time since the last charged sample).
+ * potential(d): d -= robot_radius;  d <= 0: coll_pot_multiplier * (-d) + epsilon / 2 (collision);
+ *               d <= epsilon: (d - epsilon)^2 / (2 epsilon);  else 0.
+ * The map classes of the reference (voxblox ESDF, sdf_tools) are un-vendored; the map here is a dense grid:
+ *   d_sdf[(i ny + j) nz + k] = distance at the CENTRE of cell (i, j, k), h_dims = {nx, ny, nz};
+ *   cell of a point: i = floor((x - origin_x) / resolution); centre of a cell: origin + (i + 0.5) resolution;
+ *   a point outside the grid reads oob_value.
+ * use_continuous_distance != 0 (ref use_continous_distance): inside [min_bound + map_resolution,
+ * max_bound - map_resolution] the distance is the reference's trilinear blend of the 8 cells idx +- 1 (falls back
+ * to the cell value when one of them is outside the grid); otherwise the value of the cell that holds the point.
+ * D must be 3, N 10.  d_cost [B]; optional d_is_collision [B] (1 when a charged sample was in collision),
+ * d_charged [B] (number of charged samples). */
+MINSNAP_API int minsnap_collision_cost(long B, int K, int D, int N, const double* d_coeffs,
+                                       const double* d_times, const double* d_sdf, const int32_t* h_dims,
+                                       const double* h_origin, double resolution, double oob_value,
+                                       const double* h_min_bound, const double* h_max_bound,
+                                       int use_continuous_distance, double dt, double map_resolution,
+                                       double epsilon, double robot_radius, double coll_pot_multiplier,
+                                       double* d_cost, int32_t* d_is_collision, int32_t* d_charged,
+                                       minsnap_stream_t stream);
+
 /* ---- host-buffer entry points (synchronous; copies inside) -------------------------------
  * The calls a host program makes when its data lives in host memory.  Work is cut into
  * chunks that are copied and solved on alternating streams so that PCIe and the SMs overlap.

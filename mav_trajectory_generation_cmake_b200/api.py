@@ -336,6 +336,30 @@ def optimize_segment_times(positions, times, iterations=20, time_penalty=500.0, 
     return times, torch.stack(history)
 
 
+def collision_cost(coeffs, times, sdf, origin, resolution, min_bound, max_bound, dt=0.1, map_resolution=None,
+                   epsilon=0.5, robot_radius=0.5, coll_pot_multiplier=1.0, use_continuous_distance=True, oob_value=0.0,
+                   want_charged=False):
+    """Collision cost of solved trajectories against a dense distance grid (ref getCostAndGradientCollision,
+    NL.i:1523-1709; defaults are the reference's NonlinearOptimizationParameters).  coeffs [B][K][3][10], times
+    [B][K], sdf [nx][ny][nz] (distance at the cell centres) are CUDA tensors -> dict(cost [B], is_collision [B])."""
+    torch = _torch()
+    B, K, D, N = coeffs.shape
+    if map_resolution is None:
+        map_resolution = resolution
+    dims = np.asarray(sdf.shape, np.int32)
+    org, lo, hi = _np(origin, np.float64), _np(min_bound, np.float64), _np(max_bound, np.float64)
+    cost_t = torch.empty((B,), dtype=torch.float64, device=coeffs.device)
+    hit = torch.empty((B,), dtype=torch.int32, device=coeffs.device)
+    charged = torch.empty((B,), dtype=torch.int32, device=coeffs.device) if want_charged else None
+    capi.check(_lib().minsnap_collision_cost(B, K, D, N, _dptr(coeffs, torch.float64), _dptr(times, torch.float64),
+                                             _dptr(sdf, torch.float64), _hptr(dims), _hptr(org), float(resolution),
+                                             float(oob_value), _hptr(lo), _hptr(hi), int(bool(use_continuous_distance)),
+                                             float(dt), float(map_resolution), float(epsilon), float(robot_radius),
+                                             float(coll_pot_multiplier), _dptr(cost_t), _dptr(hit), _dptr(charged),
+                                             _stream()), "minsnap_collision_cost")
+    return dict(cost=cost_t, is_collision=hit, charged=charged)
+
+
 EXTREMA_OPTIMIZATION = 0   # PolynomialOptimization::computeMaximumOfMagnitude (ref LIN.i:470-503)
 EXTREMA_TRAJECTORY = 1     # Trajectory::computeMinMaxMagnitude (ref src/trajectory.cpp:181-217)
 EXTREMA_KEEP_SMALL_COEFFICIENTS = 16   # OR into mode: do not truncate coefficients below 2.2e-16

@@ -41,6 +41,8 @@ SIGNATURES = {
                                   _vp]),
     "minsnap_time_objective": (_i, [_l, _i, _i, _i, _i, _i, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp]),
     "minsnap_time_gradient": (_i, [_l, _i, _i, _i, _i, _vp, _vp, _d, _d, _d, _vp, _vp, _vp]),
+    "minsnap_collision_cost": (_i, [_l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _i, _d, _d, _d, _d, _d, _vp, _vp,
+                                    _vp, _vp]),
     "minsnap_host_alloc": (_i, [_vp, _sz]),
     "minsnap_host_free": (_i, [_vp]),
     "minsnap_reorder_host": (_i, [_i, _i, _l, _vp, _vp, _vp]),

@@ -490,6 +490,35 @@ int minsnap_time_gradient(long B, int K, int D, int N, int derivative, const dou
   return MINSNAP_OK;
 }
 
+// collision cost against a dense distance grid (ref NL.i:1523-1709)
+int minsnap_collision_cost(long B, int K, int D, int N, const double* d_coeffs, const double* d_times,
+                           const double* d_sdf, const int32_t* h_dims, const double* h_origin, double resolution,
+                           double oob_value, const double* h_min_bound, const double* h_max_bound,
+                           int use_continuous_distance, double dt, double map_resolution, double epsilon,
+                           double robot_radius, double coll_pot_multiplier, double* d_cost, int32_t* d_is_collision,
+                           int32_t* d_charged, minsnap_stream_t stream) {
+  if (B < 0 || K < 1 || !h_dims || !h_origin || !h_min_bound || !h_max_bound || !(resolution > 0.0) || !(dt > 0.0) ||
+      !(map_resolution > 0.0) || !(epsilon > 0.0) || h_dims[0] < 1 || h_dims[1] < 1 || h_dims[2] < 1)
+    return MINSNAP_ERR_ARG;
+  if (D != 3 || N != 10) return MINSNAP_ERR_UNSUPPORTED;
+  if (B == 0) return MINSNAP_OK;
+  if (!d_coeffs || !d_times || !d_sdf || !d_cost) return MINSNAP_ERR_ARG;
+  minsnap::CollisionArgs a;
+  a.B = B; a.K = K; a.N = N; a.d_coeffs = d_coeffs; a.d_times = d_times; a.d_sdf = d_sdf;
+  a.nx = h_dims[0]; a.ny = h_dims[1]; a.nz = h_dims[2];
+  for (int k = 0; k < 3; ++k) {
+    a.origin[k] = h_origin[k];
+    a.min_bound[k] = h_min_bound[k];
+    a.max_bound[k] = h_max_bound[k];
+  }
+  a.resolution = resolution; a.oob_value = oob_value; a.use_continuous_distance = use_continuous_distance;
+  a.dt = dt; a.map_resolution = map_resolution; a.epsilon = epsilon; a.robot_radius = robot_radius;
+  a.coll_pot_multiplier = coll_pot_multiplier;
+  a.d_cost = d_cost; a.d_is_collision = d_is_collision; a.d_charged = d_charged;
+  CU(minsnap::launch_collision_cost(a, as_stream(stream)));
+  return MINSNAP_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // Host-buffer entry points
 // ---------------------------------------------------------------------------------------

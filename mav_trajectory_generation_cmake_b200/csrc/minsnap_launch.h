@@ -115,6 +115,25 @@ struct ExtremaArgs {
 int extrema_max_roots(int N, int derivative, int n_dims);
 cudaError_t launch_extrema(const ExtremaArgs& a, cudaStream_t stream);
 
+// ---- minsnap_collision.cu ---------------------------------------------------------------
+// SURVEY 8(f)3 (ref getCostAndGradientCollision NL.i:1523-1709): collision cost against a dense distance grid
+struct CollisionArgs {
+  long B;
+  int K, N;                 // D = 3
+  const double* d_coeffs;   // [B][K][3][N]
+  const double* d_times;    // [B][K]
+  const double* d_sdf;      // [nx][ny][nz], distance at the cell centres
+  int nx, ny, nz;
+  double origin[3], resolution, oob_value;
+  double min_bound[3], max_bound[3];
+  int use_continuous_distance;
+  double dt, map_resolution, epsilon, robot_radius, coll_pot_multiplier;
+  double* d_cost;           // [B]
+  int32_t* d_is_collision;  // optional [B]
+  int32_t* d_charged;       // optional [B]: number of samples that were charged
+};
+cudaError_t launch_collision_cost(const CollisionArgs& a, cudaStream_t stream);
+
 // ---- minsnap_peak.cu -------------------------------------------------------------------
 cudaError_t run_fp64_peak(int repeats, double* tflops);
 

@@ -20,7 +20,7 @@ def build(force=False):
     """Compile both oracle shared objects with oracle/Makefile (gcc, seconds)."""
     need = force or not all(
         os.path.exists(os.path.join(_LIBDIR, n)) for n in ("liboracle_f64.so", "liboracle_ld.so"))
-    src_m = max(os.path.getmtime(os.path.join(_HERE, n)) for n in ("minsnap_oracle.c", "extrema_oracle.c"))
+    src_m = max(os.path.getmtime(os.path.join(_HERE, n)) for n in ("minsnap_oracle.c", "extrema_oracle.c", "collision_oracle.c"))
     if not need:
         need = any(os.path.getmtime(os.path.join(_LIBDIR, n)) < src_m
                    for n in ("liboracle_f64.so", "liboracle_ld.so"))
@@ -274,6 +274,49 @@ class Oracle:
         d = self._dims(D, dims)
         return self.lib.orc_segment_magnitude(N, D, self._p(c), C.c_int(derivative), self._p(d), len(d),
                                               self.creal(t))
+
+
+def collision_cost(coeffs, times, sdf, origin, resolution, min_bound, max_bound, dt=0.1, map_resolution=None,
+                   epsilon=0.5, robot_radius=0.5, coll_pot_multiplier=1.0, use_continuous_distance=True, oob_value=0.0):
+    """oracle/collision_oracle.c: ref getCostAndGradientCollision (NL.i:1523-1709), one trajectory.
+    coeffs [K][3][N], times [K], sdf [nx][ny][nz] -> (cost, is_collision, n_charged)."""
+    build()
+    lib = C.CDLL(os.path.join(_LIBDIR, "liboracle_f64.so"))
+    lib.orc_collision_cost.restype = C.c_double
+    d = lambda a: np.ascontiguousarray(np.asarray(a, np.float64))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    c, t, g = d(coeffs), d(times), d(sdf)
+    K, D, N = c.shape
+    assert D == 3
+    org, lo, hi = d(origin), d(min_bound), d(max_bound)
+    if map_resolution is None:
+        map_resolution = resolution
+    hit, charged = C.c_int(), C.c_int()
+    cost = lib.orc_collision_cost(N, K, p(c), p(t), p(g), g.shape[0], g.shape[1], g.shape[2], p(org), C.c_double(resolution),
+                                  C.c_double(oob_value), p(lo), p(hi), int(bool(use_continuous_distance)), C.c_double(dt),
+                                  C.c_double(map_resolution), C.c_double(epsilon), C.c_double(robot_radius),
+                                  C.c_double(coll_pot_multiplier), C.byref(hit), C.byref(charged))
+    return cost, hit.value, charged.value
+
+
+def collision_potential(position, sdf, origin, resolution, min_bound, max_bound, map_resolution=None, epsilon=0.5,
+                        robot_radius=0.5, coll_pot_multiplier=1.0, use_continuous_distance=True, oob_value=0.0):
+    """ref getCostAndGradientPotentialESDF (NL.i:1713-1806): (cost, numeric gradient [3], is_collision)."""
+    build()
+    lib = C.CDLL(os.path.join(_LIBDIR, "liboracle_f64.so"))
+    lib.orc_collision_potential.restype = C.c_double
+    d = lambda a: np.ascontiguousarray(np.asarray(a, np.float64))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    g, org, lo, hi, pos = d(sdf), d(origin), d(min_bound), d(max_bound), d(position)
+    if map_resolution is None:
+        map_resolution = resolution
+    grad = np.zeros(3)
+    hit = C.c_int()
+    cost = lib.orc_collision_potential(p(g), g.shape[0], g.shape[1], g.shape[2], p(org), C.c_double(resolution),
+                                       C.c_double(oob_value), p(lo), p(hi), int(bool(use_continuous_distance)),
+                                       C.c_double(map_resolution), C.c_double(epsilon), C.c_double(robot_radius),
+                                       C.c_double(coll_pot_multiplier), p(pos), p(grad), C.byref(hit))
+    return cost, grad, hit.value
 
 
 def standard_mask(K, N=10, max_fixed_derivative=4):
