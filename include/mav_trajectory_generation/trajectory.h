@@ -160,14 +160,23 @@ class Trajectory {
     result->clear();
     if (sampling_times != nullptr) sampling_times->clear();
     if (segments_.empty()) return;
-    const int capacity = static_cast<int>((t_end - t_start) / dt) + 4;
+    // The reference's loop runs its accumulated time from the START OF THE SEGMENT that contains t_start
+    // (src/trajectory.cpp:104-127), so it can emit more than (t_end - t_start) / dt samples; the kernel reports
+    // the exact count and the call is repeated with that capacity when the first guess was too small.
+    int capacity = static_cast<int>((t_end - t_start) / dt) + 4;
     std::vector<double> coeffs, durations;
     pack(&coeffs, &durations);
-    std::vector<double> out(static_cast<size_t>(capacity) * D_), ts(static_cast<size_t>(capacity));
+    std::vector<double> out, ts;
     int32_t count = 0;
-    gpu::check(minsnap_evaluate_range_host(K(), D_, N_, coeffs.data(), durations.data(), t_start, t_end, dt,
-                                           derivative, capacity, out.data(), ts.data(), &count),
-               "minsnap_evaluate_range_host");
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      out.assign(static_cast<size_t>(capacity) * D_, 0.0);
+      ts.assign(static_cast<size_t>(capacity), 0.0);
+      gpu::check(minsnap_evaluate_range_host(K(), D_, N_, coeffs.data(), durations.data(), t_start, t_end, dt,
+                                             derivative, capacity, out.data(), ts.data(), &count),
+                 "minsnap_evaluate_range_host");
+      if (count <= capacity) break;
+      capacity = count;
+    }
     if (count == 0 && t_start > max_time_) LOG(ERROR) << "Start time out of range of the trajectory!";
     const int n = count < capacity ? count : capacity;
     result->reserve(static_cast<size_t>(n));

@@ -309,6 +309,24 @@ MINSNAP_API int minsnap_extrema_host(long B, int K, int D, int N, const double* 
                                      double* h_cand_times, double* h_cand_values,
                                      int32_t* h_root_count);
 
+/* ---- interchange formats -- HOST ONLY except for the sampling inside the table ---------
+ * NumPy .npy files (format 1.0, little-endian float64, C order) for the batched arrays of this header --
+ * coefficients [B][K][D][N], samples [B][M][n_deriv][D], times [B][K] -- readable by numpy.load and writable by
+ * numpy.save.  minsnap_npy_read_f64: h_data == NULL reads only ndim / shape (shape has room for 8 entries);
+ * MINSNAP_ERR_WORKSPACE when capacity (in elements) is too small, MINSNAP_ERR_UNSUPPORTED for other dtypes.
+ * minsnap_sampled_table_host: the table of ref printMatlabSampledTrajectory (NL.i:2567-2662) for one trajectory,
+ * rows [t, pos(D), vel(D), acc(D), jerk(D), snap(D), t_vertex], rows = sum_i (ceil(T_i / dt) + 1)
+ * (minsnap_sampled_table_rows; the reference uses dt = 0.01), cols = 5 D + 2, sampled on the GPU;
+ * minsnap_table_write_text writes it as whitespace-separated text with 17 significant digits. */
+MINSNAP_API int minsnap_npy_write_f64(const char* path, const double* h_data, int ndim, const int64_t* shape);
+MINSNAP_API int minsnap_npy_read_f64(const char* path, double* h_data, size_t capacity, int* ndim,
+                                     int64_t* shape);
+MINSNAP_API int minsnap_sampled_table_rows(int K, const double* h_times, double dt);
+MINSNAP_API int minsnap_sampled_table_host(int K, int D, int N, const double* h_coeffs,
+                                           const double* h_times, double dt, double* h_table,
+                                           int capacity_rows, int* rows_out, int* cols_out);
+MINSNAP_API int minsnap_table_write_text(const char* path, const double* h_table, int rows, int cols);
+
 /* ---- a3: synthetic inputs (ref: createRandomVertices, src/vertex.cpp:27-79) -- HOST ONLY ----
  * positions[b] = vertex positions of createRandomVertices(., K, pos_min, pos_max, base_seed + b):
  * std::mt19937 + one std::uniform_real_distribution<double> per axis, a vertex closer than 0.2

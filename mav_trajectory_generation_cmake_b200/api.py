@@ -562,6 +562,40 @@ def cost_host(coeffs, times, derivative=SNAP):
     return out
 
 
+def save_npy(path, array):
+    """float64 array -> .npy through the C ABI (minsnap_npy_write_f64); numpy.load reads it."""
+    a = np.ascontiguousarray(array, np.float64)
+    shape = np.asarray(a.shape, np.int64)
+    capi.check(_lib().minsnap_npy_write_f64(str(path).encode(), _hptr(a), a.ndim, _hptr(shape)), "minsnap_npy_write_f64")
+
+
+def load_npy(path):
+    """.npy (little-endian float64, C order; e.g. written by numpy.save) -> array through the C ABI."""
+    ndim = C.c_int()
+    shape = np.zeros(8, np.int64)
+    capi.check(_lib().minsnap_npy_read_f64(str(path).encode(), None, 0, C.byref(ndim), _hptr(shape)), "minsnap_npy_read_f64")
+    out = np.empty(tuple(int(x) for x in shape[: ndim.value]), np.float64)
+    capi.check(_lib().minsnap_npy_read_f64(str(path).encode(), _hptr(out), out.size, C.byref(ndim), _hptr(shape)),
+               "minsnap_npy_read_f64")
+    return out
+
+
+def sampled_table_host(coeffs, times, dt=0.01, path=None):
+    """The table of the reference's printMatlabSampledTrajectory (NL.i:2567-2662) for one trajectory:
+    coeffs [K][D][N], times [K] (host) -> [rows][5 D + 2]; written as text when path is given."""
+    coeffs = _np(coeffs, np.float64)
+    times = _np(times, np.float64)
+    K, D, N = coeffs.shape
+    rows = _lib().minsnap_sampled_table_rows(K, _hptr(times), float(dt))
+    table = np.empty((rows, 5 * D + 2), np.float64)
+    r, c = C.c_int(), C.c_int()
+    capi.check(_lib().minsnap_sampled_table_host(K, D, N, _hptr(coeffs), _hptr(times), float(dt), _hptr(table), rows,
+                                                 C.byref(r), C.byref(c)), "minsnap_sampled_table_host")
+    if path is not None:
+        capi.check(_lib().minsnap_table_write_text(str(path).encode(), _hptr(table), rows, 5 * D + 2), "minsnap_table_write_text")
+    return table
+
+
 def random_positions_host(B, K, pos_min, pos_max, base_seed):
     """Batched createRandomVertices positions (host-only workload generator): [B][K+1][D]."""
     pos_min = _np(pos_min, np.float64)

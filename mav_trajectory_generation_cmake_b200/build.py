@@ -14,7 +14,7 @@ CSRC = os.path.join(_PKG, "csrc")
 LIBDIR = os.path.join(_PKG, "lib")
 LIB = os.path.join(LIBDIR, "libminsnap_b200.so")
 
-SOURCES = ["minsnap_host_inputs.cpp", "minsnap_capi.cu", "minsnap_general.cu", "minsnap_standard.cu", "minsnap_sample.cu", "minsnap_extrema.cu",
+SOURCES = ["minsnap_host_inputs.cpp", "minsnap_interchange.cpp", "minsnap_capi.cu", "minsnap_general.cu", "minsnap_standard.cu", "minsnap_sample.cu", "minsnap_extrema.cu",
            "minsnap_peak.cu", "minsnap_collision.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

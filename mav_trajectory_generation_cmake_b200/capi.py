@@ -54,6 +54,11 @@ SIGNATURES = {
     "minsnap_estimate_segment_times_host": (_i, [_l, _i, _i, _vp, _d, _d, _d, _vp]),
     "minsnap_coeffs_from_constraints_host": (_i, [_l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "minsnap_cost_host": (_i, [_l, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "minsnap_npy_write_f64": (_i, [C.c_char_p, _vp, _i, _vp]),
+    "minsnap_npy_read_f64": (_i, [C.c_char_p, _vp, _sz, _vp, _vp]),
+    "minsnap_sampled_table_rows": (_i, [_i, _vp, _d]),
+    "minsnap_sampled_table_host": (_i, [_i, _i, _i, _vp, _vp, _d, _vp, _i, _vp, _vp]),
+    "minsnap_table_write_text": (_i, [C.c_char_p, _vp, _i, _i]),
     "minsnap_random_positions_host": (_i, [_l, _i, _i, _vp, _vp, C.c_uint64, _vp]),
     "minsnap_fp64_peak": (_i, [_i, _vp]),
 }

@@ -301,6 +301,34 @@ static void testRangeAndBatch() {
   for (size_t m = 0; m < result.size(); ++m)
     for (int d = 0; d < 3; ++d) EXPECT_LT(std::fabs(result[m][d] - singles[(m * 2 + 1) * 3 + d]), 1e-6);
 
+  // A range that starts INSIDE a segment and ends before the trajectory does: the reference's loop runs its
+  // accumulated time from the start of that segment (src/trajectory.cpp:104-127) and so emits more samples than
+  // (t_end - t_start) / dt; the mirror must return all of them (it repeats the call with the reported count).
+  {
+    const double t_start = segment_times[0] + segment_times[1] + 0.9 * segment_times[2];
+    const double t_end = t_start + 0.5, dt = 0.01;
+    size_t want = 0;   // the reference's loop, counted
+    {
+      const double seg_start = segment_times[0] + segment_times[1];
+      double accumulated = seg_start, in_segment = t_start - seg_start;
+      size_t i = 2;
+      while (accumulated < t_end) {
+        if (in_segment > segment_times[i]) {
+          in_segment = in_segment - segment_times[i];
+          if (++i >= segment_times.size()) break;
+          continue;
+        }
+        ++want;
+        in_segment += dt;
+        accumulated += dt;
+      }
+    }
+    trajectory.evaluateRange(t_start, t_end, dt, derivative_order::POSITION, &result, &sampling_times);
+    EXPECT_TRUE(want > static_cast<size_t>((t_end - t_start) / dt) + 4);
+    EXPECT_EQ(result.size(), want);
+    EXPECT_EQ(sampling_times.size(), want);
+  }
+
   // the additive batched optimizer agrees with the per-problem class
   const int B = 64, K = 10;
   std::vector<double> positions, times;
