@@ -264,7 +264,9 @@ MINSNAP_API int minsnap_collision_cost(long B, int K, int D, int N, const double
 /* ---- host-buffer entry points (synchronous; copies inside) -------------------------------
  * The calls a host program makes when its data lives in host memory.  Work is cut into
  * chunks that are copied and solved on alternating streams so that PCIe and the SMs overlap.
- * Pinned host buffers (minsnap_host_alloc) make the copies asynchronous. */
+ * Pinned host buffers (minsnap_host_alloc) make the copies asynchronous.  Calls whose buffers total at most
+ * 4 MB (one trajectory from the C++ classes) are staged through a per-thread pinned block: one copy each way.
+ * In MINSNAP_EXTREMA_OPTIMIZATION mode minsnap_extrema_host leaves h_min_* untouched. */
 MINSNAP_API int minsnap_host_alloc(void** h_ptr, size_t bytes);
 MINSNAP_API int minsnap_host_free(void* h_ptr);
 MINSNAP_API int minsnap_reorder_host(int N, int K, long n_masks, const uint8_t* h_mask,
@@ -300,6 +302,30 @@ MINSNAP_API int minsnap_coeffs_from_constraints_host(long B, int K, int D, int N
                                                      const double* h_times, double* h_coeffs);
 MINSNAP_API int minsnap_cost_host(long B, int K, int D, int N, int derivative,
                                   const double* h_coeffs, const double* h_times, double* h_cost);
+
+MINSNAP_API int minsnap_sample_uniform_host(long B, int K, int D, int N, const double* h_coeffs,
+                                            const double* h_times, int M, int n_deriv, double* h_out,
+                                            double* h_t_out);
+MINSNAP_API int minsnap_cost_sweep_host(long B, int S, int K, int D, int N, int derivative,
+                                        const double* h_positions, const double* h_end_derivatives,
+                                        const double* h_times, double* h_cost, int32_t* h_status);
+MINSNAP_API int minsnap_time_objective_host(long B, int S, int K, int D, int N, int derivative,
+                                            const double* h_positions, const double* h_end_derivatives,
+                                            const double* h_times, double time_penalty,
+                                            double* h_objective, double* h_cost, int32_t* h_status);
+MINSNAP_API int minsnap_time_gradient_host(long B, int K, int D, int N, int derivative,
+                                           const double* h_coeffs, const double* h_times,
+                                           double increment, double w_d, double w_t,
+                                           double* h_gradient, double* h_segment_cost);
+MINSNAP_API int minsnap_collision_cost_host(long B, int K, int D, int N, const double* h_coeffs,
+                                            const double* h_times, const double* h_sdf,
+                                            const int32_t* h_dims, const double* h_origin,
+                                            double resolution, double oob_value,
+                                            const double* h_min_bound, const double* h_max_bound,
+                                            int use_continuous_distance, double dt,
+                                            double map_resolution, double epsilon, double robot_radius,
+                                            double coll_pot_multiplier, double* h_cost,
+                                            int32_t* h_is_collision, int32_t* h_charged);
 
 MINSNAP_API int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs,
                                      const double* h_times, int derivative, int mode,

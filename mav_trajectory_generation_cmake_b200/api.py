@@ -562,6 +562,68 @@ def cost_host(coeffs, times, derivative=SNAP):
     return out
 
 
+def sample_uniform_host(coeffs, times, M, n_deriv=5, want_times=False):
+    coeffs, times = _np(coeffs, np.float64), _np(times, np.float64)
+    B, K, D, N = coeffs.shape
+    out = np.empty((B, M, n_deriv, D), np.float64)
+    t_out = np.empty((B, M), np.float64) if want_times else None
+    capi.check(_lib().minsnap_sample_uniform_host(B, K, D, N, _hptr(coeffs), _hptr(times), M, n_deriv, _hptr(out),
+                                                  _hptr(t_out)), "minsnap_sample_uniform_host")
+    return (out, t_out) if want_times else out
+
+
+def cost_sweep_host(positions, times, end_derivatives=None, N=10, derivative=SNAP, want_status=False):
+    """positions [B][K+1][D], times [B][S][K] (host) -> cost [B][S] (BASELINE configs[4] from host buffers)."""
+    positions, times, end_derivatives = _np(positions, np.float64), _np(times, np.float64), _np(end_derivatives, np.float64)
+    B, K1, D = positions.shape
+    S = times.shape[1]
+    out = np.empty((B, S), np.float64)
+    status = np.empty((B, S), np.int32) if want_status else None
+    capi.check(_lib().minsnap_cost_sweep_host(B, S, K1 - 1, D, N, derivative, _hptr(positions), _hptr(end_derivatives),
+                                              _hptr(times), _hptr(out), _hptr(status)), "minsnap_cost_sweep_host")
+    return (out, status) if want_status else out
+
+
+def time_objective_host(positions, times, time_penalty, end_derivatives=None, N=10, derivative=SNAP, want_cost=False):
+    positions, times, end_derivatives = _np(positions, np.float64), _np(times, np.float64), _np(end_derivatives, np.float64)
+    B, K1, D = positions.shape
+    S = times.shape[1]
+    out = np.empty((B, S), np.float64)
+    cost_a = np.empty((B, S), np.float64) if want_cost else None
+    capi.check(_lib().minsnap_time_objective_host(B, S, K1 - 1, D, N, derivative, _hptr(positions), _hptr(end_derivatives),
+                                                  _hptr(times), float(time_penalty), _hptr(out), _hptr(cost_a), None),
+               "minsnap_time_objective_host")
+    return (out, cost_a) if want_cost else out
+
+
+def time_gradient_host(coeffs, times, increment=0.1, w_d=0.1, w_t=1.0, derivative=SNAP, want_segment_cost=False):
+    coeffs, times = _np(coeffs, np.float64), _np(times, np.float64)
+    B, K, D, N = coeffs.shape
+    grad = np.empty((B, K), np.float64)
+    seg = np.empty((B, K), np.float64) if want_segment_cost else None
+    capi.check(_lib().minsnap_time_gradient_host(B, K, D, N, derivative, _hptr(coeffs), _hptr(times), float(increment),
+                                                 float(w_d), float(w_t), _hptr(grad), _hptr(seg)), "minsnap_time_gradient_host")
+    return (grad, seg) if want_segment_cost else grad
+
+
+def collision_cost_host(coeffs, times, sdf, origin, resolution, min_bound, max_bound, dt=0.1, map_resolution=None,
+                        epsilon=0.5, robot_radius=0.5, coll_pot_multiplier=1.0, use_continuous_distance=True, oob_value=0.0):
+    """numpy variant of collision_cost()."""
+    coeffs, times, sdf = _np(coeffs, np.float64), _np(times, np.float64), _np(sdf, np.float64)
+    B, K, D, N = coeffs.shape
+    if map_resolution is None:
+        map_resolution = resolution
+    dims = np.asarray(sdf.shape, np.int32)
+    org, lo, hi = _np(origin, np.float64), _np(min_bound, np.float64), _np(max_bound, np.float64)
+    cost_a, hit, charged = np.empty((B,), np.float64), np.empty((B,), np.int32), np.empty((B,), np.int32)
+    capi.check(_lib().minsnap_collision_cost_host(B, K, D, N, _hptr(coeffs), _hptr(times), _hptr(sdf), _hptr(dims), _hptr(org),
+                                                  float(resolution), float(oob_value), _hptr(lo), _hptr(hi),
+                                                  int(bool(use_continuous_distance)), float(dt), float(map_resolution),
+                                                  float(epsilon), float(robot_radius), float(coll_pot_multiplier),
+                                                  _hptr(cost_a), _hptr(hit), _hptr(charged)), "minsnap_collision_cost_host")
+    return dict(cost=cost_a, is_collision=hit, charged=charged)
+
+
 def save_npy(path, array):
     """float64 array -> .npy through the C ABI (minsnap_npy_write_f64); numpy.load reads it."""
     a = np.ascontiguousarray(array, np.float64)

@@ -39,6 +39,12 @@ SIGNATURES = {
                              _vp]),
     "minsnap_extrema_host": (_i, [_l, _i, _i, _i, _vp, _vp, _i, _i, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp]),
+    "minsnap_sample_uniform_host": (_i, [_l, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "minsnap_cost_sweep_host": (_i, [_l, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "minsnap_time_objective_host": (_i, [_l, _i, _i, _i, _i, _i, _vp, _vp, _vp, _d, _vp, _vp, _vp]),
+    "minsnap_time_gradient_host": (_i, [_l, _i, _i, _i, _i, _vp, _vp, _d, _d, _d, _vp, _vp]),
+    "minsnap_collision_cost_host": (_i, [_l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _i, _d, _d, _d, _d, _d, _vp,
+                                         _vp, _vp]),
     "minsnap_time_objective": (_i, [_l, _i, _i, _i, _i, _i, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp]),
     "minsnap_time_gradient": (_i, [_l, _i, _i, _i, _i, _vp, _vp, _d, _d, _d, _vp, _vp, _vp]),
     "minsnap_collision_cost": (_i, [_l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _i, _d, _d, _d, _d, _d, _vp, _vp,

@@ -64,24 +64,9 @@ void count_mask(const uint8_t* mask, int N, int K, int* n_fixed, int* n_free) {
   *n_free = nc - f;
 }
 
-// Stream-ordered scratch buffer (cudaMallocAsync); freed on the same stream.
-struct Scratch {
-  void* ptr = nullptr;
-  cudaStream_t stream = nullptr;
-  cudaError_t alloc(size_t bytes, cudaStream_t s) {
-    stream = s;
-    if (bytes == 0) bytes = 16;
-    return cudaMallocAsync(&ptr, bytes, s);
-  }
-  ~Scratch() {
-    if (ptr) cudaFreeAsync(ptr, stream);
-  }
-  template <typename T>
-  T* as() const { return static_cast<T*>(ptr); }
-};
-
 // Keep freed scratch memory in the device pool so that repeated host-API calls do not pay
-// for cudaMalloc each time.
+// for cudaMalloc each time.  Side effect, on purpose and process-wide: the release threshold of the
+// device's DEFAULT memory pool is raised to "never trim" (documented in INTEGRATION.md).
 void retain_pool_memory() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return;
@@ -176,68 +161,106 @@ struct HostPipeline {
 };
 thread_local HostPipeline g_pipeline;
 
-class SmallCall {
+// One host-buffer call.  The buffers are declared first -- inputs with their host source, outputs with their
+// host destination (NULL: device-only, not copied back), device-only scratch -- and run() stages them: through
+// the thread's pinned arena with ONE copy each way when the call is small (a trajectory from the C++ drop-in
+// classes), through stream-ordered allocations with one copy per buffer when it is large; it then invokes the
+// device-pointer entry point on the thread's stream and waits.  Every *_host entry point is this pattern.
+class HostCall {
  public:
-  explicit SmallCall(cudaStream_t st) : st_(st) {}
-  // declare buffers first (inputs, outputs, device-only scratch), then upload()
-  int in(const void* src, size_t bytes) { return add(ins_, const_cast<void*>(src), bytes); }
+  HostCall() : st_(cudaStreamPerThread) {}
+  ~HostCall() {
+    for (auto* v : {&ins_, &outs_, &tmps_})
+      for (auto& b : *v)
+        if (b.dptr) cudaFreeAsync(b.dptr, st_);
+  }
+  int in(const void* src, size_t bytes) { return add(ins_, const_cast<void*>(src), src ? bytes : 0); }
   int out(void* dst, size_t bytes) { return add(outs_, dst, bytes) + 1000; }
   int scratch(size_t bytes) { return add(tmps_, nullptr, bytes) + 2000; }
-  size_t total_bytes() const { return sum(ins_) + sum(outs_) + sum(tmps_); }
-  cudaError_t upload() {
+  template <typename T>
+  T* dev(int id) const {
+    const Buf& b = buf(id);
+    return reinterpret_cast<T*>(small_ ? g_arena.d + b.off : static_cast<char*>(b.dptr));
+  }
+  // device pointer of an optional buffer: NULL when the caller passed no host pointer for it
+  template <typename T>
+  T* dev_if(int id, const void* host) const { return host ? dev<T>(id) : nullptr; }
+
+  template <typename F>
+  int run(F&& launch) {
     size_t off = 0;
     for (auto& b : ins_) { b.off = off; off += pad(b.bytes); }
     in_end_ = off;
     for (auto& b : outs_) { b.off = off; off += pad(b.bytes); }
     out_end_ = off;
     for (auto& b : tmps_) { b.off = off; off += pad(b.bytes); }
-    cudaError_t e = g_arena.ensure(off ? off : 16);
-    if (e != cudaSuccess) return e;
+    small_ = off <= kSmallCallBytes;
+    if (small_) {
+      CU(g_arena.ensure(off ? off : 16));
+      for (auto& b : ins_)
+        if (b.host && b.bytes) std::memcpy(g_arena.h + b.off, b.host, b.bytes);
+      if (in_end_ > 0) CU(cudaMemcpyAsync(g_arena.d, g_arena.h, in_end_, cudaMemcpyHostToDevice, st_));
+      const int rc = launch(st_);
+      if (rc != MINSNAP_OK) return rc;
+      if (out_end_ > in_end_)
+        CU(cudaMemcpyAsync(g_arena.h + in_end_, g_arena.d + in_end_, out_end_ - in_end_, cudaMemcpyDeviceToHost, st_));
+      CU(cudaStreamSynchronize(st_));
+      for (auto& b : outs_)
+        if (b.host && b.bytes) std::memcpy(b.host, g_arena.h + b.off, b.bytes);
+      return MINSNAP_OK;
+    }
+    retain_pool_memory();   // freed blocks stay in the device's default pool between calls (process-wide setting)
+    int rc = MINSNAP_OK;
+    for (auto* v : {&ins_, &outs_, &tmps_})
+      for (auto& b : *v) {
+        const cudaError_t e = cudaMallocAsync(&b.dptr, b.bytes ? b.bytes : 16, st_);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync");
+      }
     for (auto& b : ins_)
-      if (b.host && b.bytes) std::memcpy(g_arena.h + b.off, b.host, b.bytes);
-    if (in_end_ == 0) return cudaSuccess;
-    return cudaMemcpyAsync(g_arena.d, g_arena.h, in_end_, cudaMemcpyHostToDevice, st_);
+      if (b.host && b.bytes) {
+        const cudaError_t e = cudaMemcpyAsync(b.dptr, b.host, b.bytes, cudaMemcpyHostToDevice, st_);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(H2D)"); break; }
+      }
+    if (rc == MINSNAP_OK) rc = launch(st_);
+    if (rc == MINSNAP_OK)
+      for (auto& b : outs_)
+        if (b.host && b.bytes) {
+          const cudaError_t e = cudaMemcpyAsync(b.host, b.dptr, b.bytes, cudaMemcpyDeviceToHost, st_);
+          if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemcpyAsync(D2H)"); break; }
+        }
+    const cudaError_t es = cudaStreamSynchronize(st_);
+    if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+    return rc;
   }
-  template <typename T>
-  T* dev(int id) const {
-    const Buf& b = id >= 2000 ? tmps_[id - 2000] : id >= 1000 ? outs_[id - 1000] : ins_[id];
-    return reinterpret_cast<T*>(g_arena.d + b.off);
-  }
-  template <typename T>
-  const T* host(int id) const {
-    const Buf& b = id >= 2000 ? tmps_[id - 2000] : id >= 1000 ? outs_[id - 1000] : ins_[id];
-    return reinterpret_cast<const T*>(g_arena.h + b.off);
-  }
-  // copies every output back, waits, unpacks into the caller's buffers
-  cudaError_t download() {
-    cudaError_t e = cudaSuccess;
-    if (out_end_ > in_end_)
-      e = cudaMemcpyAsync(g_arena.h + in_end_, g_arena.d + in_end_, out_end_ - in_end_, cudaMemcpyDeviceToHost, st_);
-    if (e != cudaSuccess) return e;
-    if ((e = cudaStreamSynchronize(st_)) != cudaSuccess) return e;
-    for (auto& b : outs_)
-      if (b.host && b.bytes) std::memcpy(b.host, g_arena.h + b.off, b.bytes);
-    return cudaSuccess;
+  // after run(): the first `bytes` of a device-only output (an output declared with a NULL host pointer)
+  int fetch(int id, void* dst, size_t bytes) const {
+    if (bytes == 0) return MINSNAP_OK;
+    const Buf& b = buf(id);
+    if (small_) {
+      std::memcpy(dst, g_arena.h + b.off, bytes);
+      return MINSNAP_OK;
+    }
+    CU(cudaMemcpyAsync(dst, b.dptr, bytes, cudaMemcpyDeviceToHost, st_));
+    CU(cudaStreamSynchronize(st_));
+    return MINSNAP_OK;
   }
 
  private:
   struct Buf {
     void* host;
     size_t bytes, off;
+    void* dptr;
   };
   static size_t pad(size_t b) { return (b + 255) & ~size_t(255); }
-  static size_t sum(const std::vector<Buf>& v) {
-    size_t t = 0;
-    for (auto& b : v) t += pad(b.bytes);
-    return t;
-  }
   static int add(std::vector<Buf>& v, void* host, size_t bytes) {
-    v.push_back(Buf{host, bytes, 0});
+    v.push_back(Buf{host, bytes, 0, nullptr});
     return static_cast<int>(v.size()) - 1;
   }
+  const Buf& buf(int id) const { return id >= 2000 ? tmps_[id - 2000] : id >= 1000 ? outs_[id - 1000] : ins_[id]; }
   cudaStream_t st_;
   std::vector<Buf> ins_, outs_, tmps_;
   size_t in_end_ = 0, out_end_ = 0;
+  bool small_ = true;
 };
 
 }  // namespace
@@ -539,41 +562,14 @@ int minsnap_reorder_host(int N, int K, long n_masks, const uint8_t* h_mask, int3
   if (!minsnap::supported_n(N) || K < 1 || n_masks < 0 || !h_mask || !h_col_of_row || !h_counts)
     return MINSNAP_ERR_ARG;
   if (n_masks == 0) return MINSNAP_OK;
-  {
-    SmallCall sc(cudaStreamPerThread);
-    const size_t nm = (size_t)n_masks;
-    const int i_mask = sc.in(h_mask, nm * (K + 1) * (N / 2));
-    const int o_col = sc.out(h_col_of_row, sizeof(int32_t) * nm * N * K);
-    const int o_cnt = sc.out(h_counts, sizeof(int32_t) * nm * 2);
-    if (sc.total_bytes() <= kSmallCallBytes) {
-      CU(sc.upload());
-      const int rc = minsnap_reorder(N, K, n_masks, sc.dev<uint8_t>(i_mask), sc.dev<int32_t>(o_col),
-                                     sc.dev<int32_t>(o_cnt), cudaStreamPerThread);
-      if (rc != MINSNAP_OK) return rc;
-      CU(sc.download());
-      return MINSNAP_OK;
-    }
-  }
-  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
-  int rc = MINSNAP_OK;
-  {
-    Scratch mk, col, cnt;
-    const size_t nm = (size_t)n_masks, nc = (size_t)(K + 1) * (N / 2);
-#define TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #x); goto done; } } while (0)
-    TRY(mk.alloc(nm * nc, st));
-    TRY(col.alloc(sizeof(int32_t) * nm * N * K, st));
-    TRY(cnt.alloc(sizeof(int32_t) * nm * 2, st));
-    TRY(cudaMemcpyAsync(mk.ptr, h_mask, nm * nc, cudaMemcpyHostToDevice, st));
-    rc = minsnap_reorder(N, K, n_masks, mk.as<uint8_t>(), col.as<int32_t>(), cnt.as<int32_t>(), st);
-    if (rc != MINSNAP_OK) goto done;
-    TRY(cudaMemcpyAsync(h_col_of_row, col.ptr, sizeof(int32_t) * nm * N * K, cudaMemcpyDeviceToHost, st));
-    TRY(cudaMemcpyAsync(h_counts, cnt.ptr, sizeof(int32_t) * nm * 2, cudaMemcpyDeviceToHost, st));
-#undef TRY
-  done:;
-  }
-  cudaError_t es = cudaStreamSynchronize(st);
-  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
-  return rc;
+  HostCall hc;
+  const size_t nm = (size_t)n_masks;
+  const int i_mask = hc.in(h_mask, nm * (K + 1) * (N / 2));
+  const int o_col = hc.out(h_col_of_row, sizeof(int32_t) * nm * N * K);
+  const int o_cnt = hc.out(h_counts, sizeof(int32_t) * nm * 2);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_reorder(N, K, n_masks, hc.dev<uint8_t>(i_mask), hc.dev<int32_t>(o_col), hc.dev<int32_t>(o_cnt), st);
+  });
 }
 
 int minsnap_solve_host(long B, int K, int D, int N, int derivative, const uint8_t* h_fixed_mask,
@@ -583,64 +579,23 @@ int minsnap_solve_host(long B, int K, int D, int N, int derivative, const uint8_
   int n_fixed, n_free;
   count_mask(h_fixed_mask, N, K, &n_fixed, &n_free);
   if (n_fixed > 0 && !h_fixed_values) return MINSNAP_ERR_ARG;
-  retain_pool_memory();
   if (B == 0) return MINSNAP_OK;
-  {
-    SmallCall sc(cudaStreamPerThread);
-    const size_t nb = (size_t)B;
-    const int i_fixed = sc.in(h_fixed_values, sizeof(double) * nb * n_fixed * D);
-    const int i_times = sc.in(h_times, sizeof(double) * nb * K);
-    const int o_coeffs = sc.out(h_coeffs, sizeof(double) * nb * K * D * N);
-    const int o_free = sc.out(h_free_values, sizeof(double) * nb * n_free * D);
-    const int o_cost = sc.out(h_cost, sizeof(double) * nb);
-    const int o_status = sc.out(h_status, sizeof(int32_t) * nb);
-    const int o_col = sc.out(h_col_of_row, sizeof(int32_t) * (size_t)N * K);
-    const int t_ws = sc.scratch(SolveWorkspace::bytes(N, K));
-    if (sc.total_bytes() <= kSmallCallBytes) {
-      CU(sc.upload());
-      const int rc = minsnap_solve(B, K, D, N, derivative, h_fixed_mask, sc.dev<double>(i_fixed),
-                                   sc.dev<double>(i_times), sc.dev<double>(o_coeffs), sc.dev<double>(o_free),
-                                   h_cost ? sc.dev<double>(o_cost) : nullptr, sc.dev<int32_t>(o_status),
-                                   sc.dev<int32_t>(o_col), sc.dev<char>(t_ws), SolveWorkspace::bytes(N, K),
-                                   cudaStreamPerThread);
-      if (rc != MINSNAP_OK) return rc;
-      CU(sc.download());
-      return MINSNAP_OK;
-    }
-  }
-  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
-  int rc = MINSNAP_OK;
-  {
-    Scratch fv, tm, co, fr, cs, ss, ws, cr;
-    const size_t nb = (size_t)B;
-#define TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #x); goto done; } } while (0)
-    TRY(fv.alloc(sizeof(double) * nb * n_fixed * D, st));
-    TRY(tm.alloc(sizeof(double) * nb * K, st));
-    TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
-    TRY(fr.alloc(sizeof(double) * nb * n_free * D, st));
-    TRY(cs.alloc(sizeof(double) * nb, st));
-    TRY(ss.alloc(sizeof(int32_t) * nb, st));
-    TRY(cr.alloc(sizeof(int32_t) * (size_t)N * K, st));
-    TRY(ws.alloc(SolveWorkspace::bytes(N, K), st));
-    if (n_fixed > 0)
-      TRY(cudaMemcpyAsync(fv.ptr, h_fixed_values, sizeof(double) * nb * n_fixed * D, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
-    rc = minsnap_solve(B, K, D, N, derivative, h_fixed_mask, fv.as<double>(), tm.as<double>(), co.as<double>(),
-                       fr.as<double>(), h_cost ? cs.as<double>() : nullptr, ss.as<int32_t>(), cr.as<int32_t>(),
-                       ws.ptr, SolveWorkspace::bytes(N, K), st);
-    if (rc != MINSNAP_OK) goto done;
-    TRY(cudaMemcpyAsync(h_coeffs, co.ptr, sizeof(double) * nb * K * D * N, cudaMemcpyDeviceToHost, st));
-    if (h_free_values && n_free > 0)
-      TRY(cudaMemcpyAsync(h_free_values, fr.ptr, sizeof(double) * nb * n_free * D, cudaMemcpyDeviceToHost, st));
-    if (h_cost) TRY(cudaMemcpyAsync(h_cost, cs.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
-    if (h_status) TRY(cudaMemcpyAsync(h_status, ss.ptr, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
-    if (h_col_of_row)
-      TRY(cudaMemcpyAsync(h_col_of_row, cr.ptr, sizeof(int32_t) * (size_t)N * K, cudaMemcpyDeviceToHost, st));
-  done:;
-  }
-  cudaError_t es = cudaStreamSynchronize(st);
-  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
-  return rc;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const int i_fixed = hc.in(h_fixed_values, sizeof(double) * nb * n_fixed * D);
+  const int i_times = hc.in(h_times, sizeof(double) * nb * K);
+  const int o_coeffs = hc.out(h_coeffs, sizeof(double) * nb * K * D * N);
+  const int o_free = hc.out(h_free_values, sizeof(double) * nb * n_free * D);
+  const int o_cost = hc.out(h_cost, sizeof(double) * nb);
+  const int o_status = hc.out(h_status, sizeof(int32_t) * nb);
+  const int o_col = hc.out(h_col_of_row, sizeof(int32_t) * (size_t)N * K);
+  const int t_ws = hc.scratch(SolveWorkspace::bytes(N, K));
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_solve(B, K, D, N, derivative, h_fixed_mask, hc.dev<double>(i_fixed), hc.dev<double>(i_times),
+                         hc.dev<double>(o_coeffs), hc.dev<double>(o_free), hc.dev_if<double>(o_cost, h_cost),
+                         hc.dev<int32_t>(o_status), hc.dev<int32_t>(o_col), hc.dev<char>(t_ws),
+                         SolveWorkspace::bytes(N, K), st);
+  });
 }
 
 int minsnap_coeffs_from_constraints_host(long B, int K, int D, int N, const uint8_t* h_fixed_mask,
@@ -651,88 +606,32 @@ int minsnap_coeffs_from_constraints_host(long B, int K, int D, int N, const uint
   count_mask(h_fixed_mask, N, K, &n_fixed, &n_free);
   if ((n_fixed > 0 && !h_fixed_values) || (n_free > 0 && !h_free_values)) return MINSNAP_ERR_ARG;
   if (B == 0) return MINSNAP_OK;
-  {
-    SmallCall sc(cudaStreamPerThread);
-    const size_t nb = (size_t)B;
-    const int i_fixed = sc.in(h_fixed_values, sizeof(double) * nb * n_fixed * D);
-    const int i_free = sc.in(h_free_values, sizeof(double) * nb * n_free * D);
-    const int i_times = sc.in(h_times, sizeof(double) * nb * K);
-    const int o_coeffs = sc.out(h_coeffs, sizeof(double) * nb * K * D * N);
-    const int t_ws = sc.scratch(SolveWorkspace::bytes(N, K));
-    if (sc.total_bytes() <= kSmallCallBytes) {
-      CU(sc.upload());
-      const int rc = minsnap_coeffs_from_constraints(B, K, D, N, h_fixed_mask, sc.dev<double>(i_fixed),
-                                                     sc.dev<double>(i_free), sc.dev<double>(i_times),
-                                                     sc.dev<double>(o_coeffs), sc.dev<char>(t_ws),
-                                                     SolveWorkspace::bytes(N, K), cudaStreamPerThread);
-      if (rc != MINSNAP_OK) return rc;
-      CU(sc.download());
-      return MINSNAP_OK;
-    }
-  }
-  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
-  int rc = MINSNAP_OK;
-  {
-    Scratch fv, fr, tm, co, ws;
-    const size_t nb = (size_t)B;
-    TRY(fv.alloc(sizeof(double) * nb * n_fixed * D, st));
-    TRY(fr.alloc(sizeof(double) * nb * n_free * D, st));
-    TRY(tm.alloc(sizeof(double) * nb * K, st));
-    TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
-    TRY(ws.alloc(SolveWorkspace::bytes(N, K), st));
-    if (n_fixed > 0)
-      TRY(cudaMemcpyAsync(fv.ptr, h_fixed_values, sizeof(double) * nb * n_fixed * D, cudaMemcpyHostToDevice, st));
-    if (n_free > 0)
-      TRY(cudaMemcpyAsync(fr.ptr, h_free_values, sizeof(double) * nb * n_free * D, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
-    rc = minsnap_coeffs_from_constraints(B, K, D, N, h_fixed_mask, fv.as<double>(), fr.as<double>(),
-                                         tm.as<double>(), co.as<double>(), ws.ptr, SolveWorkspace::bytes(N, K), st);
-    if (rc != MINSNAP_OK) goto done;
-    TRY(cudaMemcpyAsync(h_coeffs, co.ptr, sizeof(double) * nb * K * D * N, cudaMemcpyDeviceToHost, st));
-  done:;
-  }
-  cudaError_t es = cudaStreamSynchronize(st);
-  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
-  return rc;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const int i_fixed = hc.in(h_fixed_values, sizeof(double) * nb * n_fixed * D);
+  const int i_free = hc.in(h_free_values, sizeof(double) * nb * n_free * D);
+  const int i_times = hc.in(h_times, sizeof(double) * nb * K);
+  const int o_coeffs = hc.out(h_coeffs, sizeof(double) * nb * K * D * N);
+  const int t_ws = hc.scratch(SolveWorkspace::bytes(N, K));
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_coeffs_from_constraints(B, K, D, N, h_fixed_mask, hc.dev<double>(i_fixed), hc.dev<double>(i_free),
+                                           hc.dev<double>(i_times), hc.dev<double>(o_coeffs), hc.dev<char>(t_ws),
+                                           SolveWorkspace::bytes(N, K), st);
+  });
 }
 
 int minsnap_cost_host(long B, int K, int D, int N, int derivative, const double* h_coeffs, const double* h_times,
                       double* h_cost) {
   if (!shape_ok(B, K, D, N, derivative) || !h_coeffs || !h_times || !h_cost) return MINSNAP_ERR_ARG;
   if (B == 0) return MINSNAP_OK;
-  {
-    SmallCall sc(cudaStreamPerThread);
-    const size_t nb = (size_t)B;
-    const int i_coeffs = sc.in(h_coeffs, sizeof(double) * nb * K * D * N);
-    const int i_times = sc.in(h_times, sizeof(double) * nb * K);
-    const int o_cost = sc.out(h_cost, sizeof(double) * nb);
-    if (sc.total_bytes() <= kSmallCallBytes) {
-      CU(sc.upload());
-      const int rc = minsnap_cost(B, K, D, N, derivative, sc.dev<double>(i_coeffs), sc.dev<double>(i_times),
-                                  sc.dev<double>(o_cost), cudaStreamPerThread);
-      if (rc != MINSNAP_OK) return rc;
-      CU(sc.download());
-      return MINSNAP_OK;
-    }
-  }
-  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
-  int rc = MINSNAP_OK;
-  {
-    Scratch co, tm, cs;
-    const size_t nb = (size_t)B;
-    TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
-    TRY(tm.alloc(sizeof(double) * nb * K, st));
-    TRY(cs.alloc(sizeof(double) * nb, st));
-    TRY(cudaMemcpyAsync(co.ptr, h_coeffs, sizeof(double) * nb * K * D * N, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
-    rc = minsnap_cost(B, K, D, N, derivative, co.as<double>(), tm.as<double>(), cs.as<double>(), st);
-    if (rc != MINSNAP_OK) goto done;
-    TRY(cudaMemcpyAsync(h_cost, cs.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
-  done:;
-  }
-  cudaError_t es = cudaStreamSynchronize(st);
-  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
-  return rc;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const int i_coeffs = hc.in(h_coeffs, sizeof(double) * nb * K * D * N);
+  const int i_times = hc.in(h_times, sizeof(double) * nb * K);
+  const int o_cost = hc.out(h_cost, sizeof(double) * nb);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_cost(B, K, D, N, derivative, hc.dev<double>(i_coeffs), hc.dev<double>(i_times), hc.dev<double>(o_cost), st);
+  });
 }
 
 int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs, const double* h_times, int derivative,
@@ -745,75 +644,30 @@ int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs, co
   const size_t nb = (size_t)B;
   const size_t max_roots = (size_t)minsnap::extrema_max_roots(N, derivative, __builtin_popcount(dim_mask));
   const size_t cand_bytes = sizeof(double) * nb * K * (max_roots + 2);
-  {
-    SmallCall sc(cudaStreamPerThread);
-    const int i_coeffs = sc.in(h_coeffs, sizeof(double) * nb * K * D * N);
-    const int i_times = sc.in(h_times, sizeof(double) * nb * K);
-    const int o_xt = sc.out(h_max_time, sizeof(double) * nb);
-    const int o_xv = sc.out(h_max_value, sizeof(double) * nb);
-    const int o_xs = sc.out(h_max_segment, sizeof(int32_t) * nb);
-    const int o_nt = sc.out(h_min_time, sizeof(double) * nb);
-    const int o_nv = sc.out(h_min_value, sizeof(double) * nb);
-    const int o_ns = sc.out(h_min_segment, sizeof(int32_t) * nb);
-    const int o_ct = h_cand_times ? sc.out(h_cand_times, cand_bytes) : -1;
-    const int o_cv = h_cand_values ? sc.out(h_cand_values, cand_bytes) : -1;
-    const int o_rc = h_root_count ? sc.out(h_root_count, sizeof(int32_t) * nb * K) : -1;
-    if (sc.total_bytes() <= kSmallCallBytes) {
-      CU(sc.upload());
-      const int rc = minsnap_extrema(B, K, D, N, sc.dev<double>(i_coeffs), sc.dev<double>(i_times), derivative, mode,
-                                     dim_mask, sc.dev<double>(o_xt), sc.dev<double>(o_xv), sc.dev<int32_t>(o_xs),
-                                     sc.dev<double>(o_nt), sc.dev<double>(o_nv), sc.dev<int32_t>(o_ns),
-                                     o_ct >= 0 ? sc.dev<double>(o_ct) : nullptr,
-                                     o_cv >= 0 ? sc.dev<double>(o_cv) : nullptr,
-                                     o_rc >= 0 ? sc.dev<int32_t>(o_rc) : nullptr, cudaStreamPerThread);
-      if (rc != MINSNAP_OK) return rc;
-      CU(sc.download());
-      return MINSNAP_OK;
-    }
-  }
-  cudaStream_t st = cudaStreamPerThread;
-  int rc = MINSNAP_OK;
-  {
-    Scratch co, tm, xt, xv, xs, nt, nv, ns, ctm, cvl, rcnt;
-    TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
-    TRY(tm.alloc(sizeof(double) * nb * K, st));
-    TRY(xt.alloc(sizeof(double) * nb, st));
-    TRY(xv.alloc(sizeof(double) * nb, st));
-    TRY(xs.alloc(sizeof(int32_t) * nb, st));
-    TRY(nt.alloc(sizeof(double) * nb, st));
-    TRY(nv.alloc(sizeof(double) * nb, st));
-    TRY(ns.alloc(sizeof(int32_t) * nb, st));
-    if (h_cand_times) TRY(ctm.alloc(cand_bytes, st));
-    if (h_cand_values) TRY(cvl.alloc(cand_bytes, st));
-    if (h_root_count) TRY(rcnt.alloc(sizeof(int32_t) * nb * K, st));
-    TRY(cudaMemcpyAsync(co.ptr, h_coeffs, sizeof(double) * nb * K * D * N, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
-    rc = minsnap_extrema(B, K, D, N, co.as<double>(), tm.as<double>(), derivative, mode, dim_mask, xt.as<double>(),
-                         xv.as<double>(), xs.as<int32_t>(), nt.as<double>(), nv.as<double>(), ns.as<int32_t>(),
-                         h_cand_times ? ctm.as<double>() : nullptr, h_cand_values ? cvl.as<double>() : nullptr,
-                         h_root_count ? rcnt.as<int32_t>() : nullptr, st);
-    if (rc != MINSNAP_OK) goto done;
-    if (h_max_time) TRY(cudaMemcpyAsync(h_max_time, xt.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
-    if (h_max_value) TRY(cudaMemcpyAsync(h_max_value, xv.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
-    if (h_max_segment) TRY(cudaMemcpyAsync(h_max_segment, xs.ptr, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
-    if ((mode & ~MINSNAP_EXTREMA_KEEP_SMALL_COEFFICIENTS) == MINSNAP_EXTREMA_TRAJECTORY) {
-      if (h_min_time) TRY(cudaMemcpyAsync(h_min_time, nt.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
-      if (h_min_value) TRY(cudaMemcpyAsync(h_min_value, nv.ptr, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
-      if (h_min_segment) TRY(cudaMemcpyAsync(h_min_segment, ns.ptr, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
-    }
-    if (h_cand_times) TRY(cudaMemcpyAsync(h_cand_times, ctm.ptr, cand_bytes, cudaMemcpyDeviceToHost, st));
-    if (h_cand_values) TRY(cudaMemcpyAsync(h_cand_values, cvl.ptr, cand_bytes, cudaMemcpyDeviceToHost, st));
-    if (h_root_count)
-      TRY(cudaMemcpyAsync(h_root_count, rcnt.ptr, sizeof(int32_t) * nb * K, cudaMemcpyDeviceToHost, st));
-  done:;
-  }
-  cudaError_t es = cudaStreamSynchronize(st);
-  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
-  return rc;
+  // the minimum is produced in trajectory mode only: in optimisation mode the caller's h_min_* stay untouched
+  const bool with_min = (mode & ~MINSNAP_EXTREMA_KEEP_SMALL_COEFFICIENTS) == MINSNAP_EXTREMA_TRAJECTORY;
+  HostCall hc;
+  const int i_coeffs = hc.in(h_coeffs, sizeof(double) * nb * K * D * N);
+  const int i_times = hc.in(h_times, sizeof(double) * nb * K);
+  const int o_xt = hc.out(h_max_time, sizeof(double) * nb);
+  const int o_xv = hc.out(h_max_value, sizeof(double) * nb);
+  const int o_xs = hc.out(h_max_segment, sizeof(int32_t) * nb);
+  const int o_nt = hc.out(with_min ? h_min_time : nullptr, sizeof(double) * nb);
+  const int o_nv = hc.out(with_min ? h_min_value : nullptr, sizeof(double) * nb);
+  const int o_ns = hc.out(with_min ? h_min_segment : nullptr, sizeof(int32_t) * nb);
+  const int o_ct = hc.out(h_cand_times, h_cand_times ? cand_bytes : 0);
+  const int o_cv = hc.out(h_cand_values, h_cand_values ? cand_bytes : 0);
+  const int o_rc = hc.out(h_root_count, h_root_count ? sizeof(int32_t) * nb * K : 0);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_extrema(B, K, D, N, hc.dev<double>(i_coeffs), hc.dev<double>(i_times), derivative, mode, dim_mask,
+                           hc.dev<double>(o_xt), hc.dev<double>(o_xv), hc.dev<int32_t>(o_xs), hc.dev<double>(o_nt),
+                           hc.dev<double>(o_nv), hc.dev<int32_t>(o_ns), hc.dev_if<double>(o_ct, h_cand_times),
+                           hc.dev_if<double>(o_cv, h_cand_values), hc.dev_if<int32_t>(o_rc, h_root_count), st);
+  });
 }
 
-// Chunked, double-buffered pipeline: while chunk c is being solved, chunk c+1 is on its way
-// in and chunk c-1 on its way out (two streams, each with its own device buffers).
+// Large batches: a chunked copy / solve / copy pipeline of three stages on the thread's persistent streams
+// (HostPipeline above); small ones: one staged call.
 int minsnap_solve_standard_host(long B, int K, int D, int N, int derivative, const double* h_positions,
                                 const double* h_end_derivatives, const double* h_times, double v_max,
                                 double a_max, double magic, double* h_times_out, double* h_coeffs,
@@ -823,32 +677,32 @@ int minsnap_solve_standard_host(long B, int K, int D, int N, int derivative, con
   if (!h_positions || !h_coeffs) return MINSNAP_ERR_ARG;
   if (!h_times && !(v_max > 0.0 && a_max > 0.0)) return MINSNAP_ERR_ARG;
   {
-    SmallCall sc(cudaStreamPerThread);
     const size_t nb = (size_t)B;
     const int hh = N / 2;
     const size_t n_free_s = (size_t)(K > 1 ? (K - 1) * (hh - 1) : 0);
-    const int i_pos = sc.in(h_positions, sizeof(double) * nb * (K + 1) * D);
-    const int i_end = sc.in(h_end_derivatives, h_end_derivatives ? sizeof(double) * nb * 2 * (hh - 1) * D : 0);
-    const int i_tm = sc.in(h_times, h_times ? sizeof(double) * nb * K : 0);
-    const int o_tm = sc.out(h_times ? nullptr : h_times_out, sizeof(double) * nb * K);
-    const int o_coeffs = sc.out(h_coeffs, sizeof(double) * nb * K * D * N);
-    const int o_free = sc.out(h_free_values, h_free_values ? sizeof(double) * nb * n_free_s * D : 0);
-    const int o_cost = sc.out(h_cost, h_cost ? sizeof(double) * nb : 0);
-    const int o_status = sc.out(h_status, h_status ? sizeof(int32_t) * nb : 0);
-    if (sc.total_bytes() <= kSmallCallBytes) {
-      CU(sc.upload());
-      const int rc = minsnap_solve_standard(
-          B, K, D, N, derivative, sc.dev<double>(i_pos), h_end_derivatives ? sc.dev<double>(i_end) : nullptr,
-          h_times ? sc.dev<double>(i_tm) : nullptr, v_max, a_max, magic,
-          (!h_times && h_times_out) ? sc.dev<double>(o_tm) : nullptr, sc.dev<double>(o_coeffs),
-          h_free_values ? sc.dev<double>(o_free) : nullptr, h_cost ? sc.dev<double>(o_cost) : nullptr,
-          h_status ? sc.dev<int32_t>(o_status) : nullptr, cudaStreamPerThread);
-      if (rc != MINSNAP_OK) return rc;
-      CU(sc.download());
-      if (h_times && h_times_out) std::memcpy(h_times_out, h_times, sizeof(double) * nb * K);
-      return MINSNAP_OK;
+    const size_t total = sizeof(double) * nb * ((K + 1) * D + 2 * (hh - 1) * D + 2 * K + K * D * N + n_free_s * D + 1) + 4 * nb;
+    if (total + 4096 <= kSmallCallBytes) {
+      HostCall hc;
+      const int i_pos = hc.in(h_positions, sizeof(double) * nb * (K + 1) * D);
+      const int i_end = hc.in(h_end_derivatives, sizeof(double) * nb * 2 * (hh - 1) * D);
+      const int i_tm = hc.in(h_times, sizeof(double) * nb * K);
+      const int o_tm = hc.out(h_times ? nullptr : h_times_out, sizeof(double) * nb * K);
+      const int o_coeffs = hc.out(h_coeffs, sizeof(double) * nb * K * D * N);
+      const int o_free = hc.out(h_free_values, h_free_values ? sizeof(double) * nb * n_free_s * D : 0);
+      const int o_cost = hc.out(h_cost, h_cost ? sizeof(double) * nb : 0);
+      const int o_status = hc.out(h_status, h_status ? sizeof(int32_t) * nb : 0);
+      const int rc = hc.run([&](cudaStream_t st) {
+        return minsnap_solve_standard(B, K, D, N, derivative, hc.dev<double>(i_pos),
+                                      hc.dev_if<double>(i_end, h_end_derivatives), hc.dev_if<double>(i_tm, h_times), v_max,
+                                      a_max, magic, (!h_times && h_times_out) ? hc.dev<double>(o_tm) : nullptr,
+                                      hc.dev<double>(o_coeffs), hc.dev_if<double>(o_free, h_free_values),
+                                      hc.dev_if<double>(o_cost, h_cost), hc.dev_if<int32_t>(o_status, h_status), st);
+      });
+      if (rc == MINSNAP_OK && h_times && h_times_out) std::memcpy(h_times_out, h_times, sizeof(double) * nb * K);
+      return rc;
     }
   }
+#define TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #x); goto done; } } while (0)
   const int h = N / 2;
   const int n_free = (K - 1) * (h - 1);
   // chunk = unit of the copy/solve/copy pipeline (MINSNAP_TUNE_HOST_CHUNK overrides for measurements)
@@ -918,55 +772,43 @@ int minsnap_solve_standard_host(long B, int K, int D, int N, int derivative, con
   return rc;
 }
 
+#undef TRY
+
 int minsnap_sample_at_host(long B, int K, int D, int N, const double* h_coeffs, const double* h_times, int M,
                            const double* h_t, long t_stride, int n_deriv, double* h_out, int32_t* h_segment) {
   if (B < 0 || K < 1 || D < 1 || !minsnap::supported_n(N) || M < 0 || n_deriv < 1 || !h_coeffs || !h_times ||
       !h_t || !h_out || (t_stride != 0 && t_stride < M))
     return MINSNAP_ERR_ARG;
   if (B == 0 || M == 0) return MINSNAP_OK;
-  {
-    SmallCall sc(cudaStreamPerThread);
-    const size_t nb = (size_t)B;
-    const size_t n_t = t_stride == 0 ? (size_t)M : nb * (size_t)t_stride;
-    const int i_coeffs = sc.in(h_coeffs, sizeof(double) * nb * K * D * N);
-    const int i_times = sc.in(h_times, sizeof(double) * nb * K);
-    const int i_t = sc.in(h_t, sizeof(double) * n_t);
-    const int o_out = sc.out(h_out, sizeof(double) * nb * M * n_deriv * D);
-    const int o_seg = sc.out(h_segment, sizeof(int32_t) * nb * M);
-    if (sc.total_bytes() <= kSmallCallBytes) {
-      CU(sc.upload());
-      const int rc = minsnap_sample_at(B, K, D, N, sc.dev<double>(i_coeffs), sc.dev<double>(i_times), M,
-                                       sc.dev<double>(i_t), t_stride, n_deriv, sc.dev<double>(o_out),
-                                       h_segment ? sc.dev<int32_t>(o_seg) : nullptr, cudaStreamPerThread);
-      if (rc != MINSNAP_OK) return rc;
-      CU(sc.download());
-      return MINSNAP_OK;
-    }
-  }
-  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
-  int rc = MINSNAP_OK;
-  {
-    Scratch co, tm, tt, out, sg;
-    const size_t nb = (size_t)B;
-    const size_t n_t = t_stride == 0 ? (size_t)M : nb * (size_t)t_stride;
-    TRY(co.alloc(sizeof(double) * nb * K * D * N, st));
-    TRY(tm.alloc(sizeof(double) * nb * K, st));
-    TRY(tt.alloc(sizeof(double) * n_t, st));
-    TRY(out.alloc(sizeof(double) * nb * M * n_deriv * D, st));
-    TRY(sg.alloc(sizeof(int32_t) * nb * M, st));
-    TRY(cudaMemcpyAsync(co.ptr, h_coeffs, sizeof(double) * nb * K * D * N, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * nb * K, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(tt.ptr, h_t, sizeof(double) * n_t, cudaMemcpyHostToDevice, st));
-    rc = minsnap_sample_at(B, K, D, N, co.as<double>(), tm.as<double>(), M, tt.as<double>(), t_stride, n_deriv,
-                           out.as<double>(), h_segment ? sg.as<int32_t>() : nullptr, st);
-    if (rc != MINSNAP_OK) goto done;
-    TRY(cudaMemcpyAsync(h_out, out.ptr, sizeof(double) * nb * M * n_deriv * D, cudaMemcpyDeviceToHost, st));
-    if (h_segment) TRY(cudaMemcpyAsync(h_segment, sg.ptr, sizeof(int32_t) * nb * M, cudaMemcpyDeviceToHost, st));
-  done:;
-  }
-  cudaError_t es = cudaStreamSynchronize(st);
-  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
-  return rc;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const size_t n_t = t_stride == 0 ? (size_t)M : nb * (size_t)t_stride;
+  const int i_coeffs = hc.in(h_coeffs, sizeof(double) * nb * K * D * N);
+  const int i_times = hc.in(h_times, sizeof(double) * nb * K);
+  const int i_t = hc.in(h_t, sizeof(double) * n_t);
+  const int o_out = hc.out(h_out, sizeof(double) * nb * M * n_deriv * D);
+  const int o_seg = hc.out(h_segment, h_segment ? sizeof(int32_t) * nb * M : 0);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_sample_at(B, K, D, N, hc.dev<double>(i_coeffs), hc.dev<double>(i_times), M, hc.dev<double>(i_t),
+                             t_stride, n_deriv, hc.dev<double>(o_out), hc.dev_if<int32_t>(o_seg, h_segment), st);
+  });
+}
+
+int minsnap_sample_uniform_host(long B, int K, int D, int N, const double* h_coeffs, const double* h_times, int M,
+                                int n_deriv, double* h_out, double* h_t_out) {
+  if (B < 0 || K < 1 || D < 1 || !minsnap::supported_n(N) || M < 0 || n_deriv < 1 || !h_coeffs || !h_times || !h_out)
+    return MINSNAP_ERR_ARG;
+  if (B == 0 || M == 0) return MINSNAP_OK;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const int i_coeffs = hc.in(h_coeffs, sizeof(double) * nb * K * D * N);
+  const int i_times = hc.in(h_times, sizeof(double) * nb * K);
+  const int o_out = hc.out(h_out, sizeof(double) * nb * M * n_deriv * D);
+  const int o_t = hc.out(h_t_out, h_t_out ? sizeof(double) * nb * M : 0);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_sample_uniform(B, K, D, N, hc.dev<double>(i_coeffs), hc.dev<double>(i_times), M, n_deriv,
+                                  hc.dev<double>(o_out), hc.dev_if<double>(o_t, h_t_out), st);
+  });
 }
 
 int minsnap_evaluate_range_host(int K, int D, int N, const double* h_coeffs, const double* h_times, double t_start,
@@ -975,54 +817,21 @@ int minsnap_evaluate_range_host(int K, int D, int N, const double* h_coeffs, con
   if (K < 1 || D < 1 || !minsnap::supported_n(N) || !(dt > 0.0) || derivative < 0 || max_samples < 0 || !h_coeffs ||
       !h_times || !h_out || !h_count)
     return MINSNAP_ERR_ARG;
-  {
-    SmallCall sc(cudaStreamPerThread);
-    const int i_coeffs = sc.in(h_coeffs, sizeof(double) * (size_t)K * D * N);
-    const int i_times = sc.in(h_times, sizeof(double) * (size_t)K);
-    const int o_out = sc.out(nullptr, sizeof(double) * (size_t)max_samples * D);
-    const int o_t = sc.out(nullptr, sizeof(double) * (size_t)max_samples);
-    const int o_cnt = sc.out(h_count, sizeof(int32_t));
-    if (sc.total_bytes() <= kSmallCallBytes) {
-      CU(sc.upload());
-      const int rc = minsnap_evaluate_range(1, K, D, N, sc.dev<double>(i_coeffs), sc.dev<double>(i_times), t_start,
-                                            t_end, dt, derivative, max_samples, sc.dev<double>(o_out),
-                                            sc.dev<double>(o_t), sc.dev<int32_t>(o_cnt), cudaStreamPerThread);
-      if (rc != MINSNAP_OK) return rc;
-      CU(sc.download());
-      // only the emitted samples are meaningful: copy those out of the staging block
-      const size_t n_emit = (size_t)std::min(*h_count, max_samples);
-      std::memcpy(h_out, sc.host<double>(o_out), sizeof(double) * n_emit * D);
-      if (h_t_out) std::memcpy(h_t_out, sc.host<double>(o_t), sizeof(double) * n_emit);
-      return MINSNAP_OK;
-    }
-  }
-  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
-  int rc = MINSNAP_OK;
-  {
-    Scratch co, tm, out, tt, cnt;
-    TRY(co.alloc(sizeof(double) * (size_t)K * D * N, st));
-    TRY(tm.alloc(sizeof(double) * K, st));
-    TRY(out.alloc(sizeof(double) * (size_t)max_samples * D, st));
-    TRY(tt.alloc(sizeof(double) * (size_t)max_samples, st));
-    TRY(cnt.alloc(sizeof(int32_t), st));
-    TRY(cudaMemcpyAsync(co.ptr, h_coeffs, sizeof(double) * (size_t)K * D * N, cudaMemcpyHostToDevice, st));
-    TRY(cudaMemcpyAsync(tm.ptr, h_times, sizeof(double) * K, cudaMemcpyHostToDevice, st));
-    rc = minsnap_evaluate_range(1, K, D, N, co.as<double>(), tm.as<double>(), t_start, t_end, dt, derivative,
-                                max_samples, out.as<double>(), tt.as<double>(), cnt.as<int32_t>(), st);
-    if (rc != MINSNAP_OK) goto done;
-    TRY(cudaMemcpyAsync(h_count, cnt.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    TRY(cudaStreamSynchronize(st));
-    {
-      const size_t n = (size_t)std::min(*h_count, max_samples);
-      if (n > 0) {
-        TRY(cudaMemcpyAsync(h_out, out.ptr, sizeof(double) * n * D, cudaMemcpyDeviceToHost, st));
-        if (h_t_out) TRY(cudaMemcpyAsync(h_t_out, tt.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-      }
-    }
-  done:;
-  }
-  cudaError_t es = cudaStreamSynchronize(st);
-  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
+  HostCall hc;
+  const int i_coeffs = hc.in(h_coeffs, sizeof(double) * (size_t)K * D * N);
+  const int i_times = hc.in(h_times, sizeof(double) * (size_t)K);
+  const int o_out = hc.out(nullptr, sizeof(double) * (size_t)max_samples * D);   // fetched below: only the emitted samples
+  const int o_t = hc.out(nullptr, sizeof(double) * (size_t)max_samples);
+  const int o_cnt = hc.out(h_count, sizeof(int32_t));
+  int rc = hc.run([&](cudaStream_t st) {
+    return minsnap_evaluate_range(1, K, D, N, hc.dev<double>(i_coeffs), hc.dev<double>(i_times), t_start, t_end, dt,
+                                  derivative, max_samples, hc.dev<double>(o_out), hc.dev<double>(o_t),
+                                  hc.dev<int32_t>(o_cnt), st);
+  });
+  if (rc != MINSNAP_OK) return rc;
+  const size_t n_emit = (size_t)std::max(0, std::min(*h_count, max_samples));
+  if ((rc = hc.fetch(o_out, h_out, sizeof(double) * n_emit * D)) != MINSNAP_OK) return rc;
+  if (h_t_out) rc = hc.fetch(o_t, h_t_out, sizeof(double) * n_emit);
   return rc;
 }
 
@@ -1030,84 +839,111 @@ int minsnap_segment_matrices_host(long n, int N, int derivative, const double* h
                                   double* h_Q, double* h_H) {
   if (n < 0 || !minsnap::supported_n(N) || derivative < 0 || derivative > N / 2 - 1 || !h_T) return MINSNAP_ERR_ARG;
   if (n == 0) return MINSNAP_OK;
-  {
-    SmallCall sc(cudaStreamPerThread);
-    const size_t mat = sizeof(double) * (size_t)n * N * N;
-    const int i_T = sc.in(h_T, sizeof(double) * (size_t)n);
-    const int o_A = sc.out(h_A, h_A ? mat : 0), o_Ai = sc.out(h_Ainv, h_Ainv ? mat : 0);
-    const int o_Q = sc.out(h_Q, h_Q ? mat : 0), o_H = sc.out(h_H, h_H ? mat : 0);
-    if (sc.total_bytes() <= kSmallCallBytes) {
-      CU(sc.upload());
-      const int rc = minsnap_segment_matrices(n, N, derivative, sc.dev<double>(i_T), h_A ? sc.dev<double>(o_A) : nullptr,
-                                              h_Ainv ? sc.dev<double>(o_Ai) : nullptr,
-                                              h_Q ? sc.dev<double>(o_Q) : nullptr, h_H ? sc.dev<double>(o_H) : nullptr,
-                                              cudaStreamPerThread);
-      if (rc != MINSNAP_OK) return rc;
-      CU(sc.download());
-      return MINSNAP_OK;
-    }
-  }
-  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
-  int rc = MINSNAP_OK;
-  {
-    Scratch T, A, Ai, Q, H;
-    const size_t mat = sizeof(double) * (size_t)n * N * N;
-    TRY(T.alloc(sizeof(double) * (size_t)n, st));
-    if (h_A) TRY(A.alloc(mat, st));
-    if (h_Ainv) TRY(Ai.alloc(mat, st));
-    if (h_Q) TRY(Q.alloc(mat, st));
-    if (h_H) TRY(H.alloc(mat, st));
-    TRY(cudaMemcpyAsync(T.ptr, h_T, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
-    rc = minsnap_segment_matrices(n, N, derivative, T.as<double>(), A.as<double>(), Ai.as<double>(), Q.as<double>(),
-                                  H.as<double>(), st);
-    if (rc != MINSNAP_OK) goto done;
-    if (h_A) TRY(cudaMemcpyAsync(h_A, A.ptr, mat, cudaMemcpyDeviceToHost, st));
-    if (h_Ainv) TRY(cudaMemcpyAsync(h_Ainv, Ai.ptr, mat, cudaMemcpyDeviceToHost, st));
-    if (h_Q) TRY(cudaMemcpyAsync(h_Q, Q.ptr, mat, cudaMemcpyDeviceToHost, st));
-    if (h_H) TRY(cudaMemcpyAsync(h_H, H.ptr, mat, cudaMemcpyDeviceToHost, st));
-  done:;
-  }
-  cudaError_t es = cudaStreamSynchronize(st);
-  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
-  return rc;
+  HostCall hc;
+  const size_t mat = sizeof(double) * (size_t)n * N * N;
+  const int i_T = hc.in(h_T, sizeof(double) * (size_t)n);
+  const int o_A = hc.out(h_A, h_A ? mat : 0), o_Ai = hc.out(h_Ainv, h_Ainv ? mat : 0);
+  const int o_Q = hc.out(h_Q, h_Q ? mat : 0), o_H = hc.out(h_H, h_H ? mat : 0);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_segment_matrices(n, N, derivative, hc.dev<double>(i_T), hc.dev_if<double>(o_A, h_A),
+                                    hc.dev_if<double>(o_Ai, h_Ainv), hc.dev_if<double>(o_Q, h_Q),
+                                    hc.dev_if<double>(o_H, h_H), st);
+  });
 }
 
 int minsnap_estimate_segment_times_host(long B, int K, int D, const double* h_positions, double v_max,
                                         double a_max, double magic, double* h_times) {
   if (B < 0 || K < 1 || D < 1 || !h_positions || !h_times) return MINSNAP_ERR_ARG;
   if (B == 0) return MINSNAP_OK;
-  {
-    SmallCall sc(cudaStreamPerThread);
-    const size_t nb = (size_t)B;
-    const int i_pos = sc.in(h_positions, sizeof(double) * nb * (K + 1) * D);
-    const int o_times = sc.out(h_times, sizeof(double) * nb * K);
-    if (sc.total_bytes() <= kSmallCallBytes) {
-      CU(sc.upload());
-      const int rc = minsnap_estimate_segment_times(B, K, D, sc.dev<double>(i_pos), v_max, a_max, magic,
-                                                    sc.dev<double>(o_times), cudaStreamPerThread);
-      if (rc != MINSNAP_OK) return rc;
-      CU(sc.download());
-      return MINSNAP_OK;
-    }
-  }
-  cudaStream_t st = cudaStreamPerThread;   // no stream creation per call; re-entrant across host threads
-  int rc = MINSNAP_OK;
-  {
-    Scratch pos, tm;
-    const size_t nb = (size_t)B;
-    TRY(pos.alloc(sizeof(double) * nb * (K + 1) * D, st));
-    TRY(tm.alloc(sizeof(double) * nb * K, st));
-    TRY(cudaMemcpyAsync(pos.ptr, h_positions, sizeof(double) * nb * (K + 1) * D, cudaMemcpyHostToDevice, st));
-    rc = minsnap_estimate_segment_times(B, K, D, pos.as<double>(), v_max, a_max, magic, tm.as<double>(), st);
-    if (rc != MINSNAP_OK) goto done;
-    TRY(cudaMemcpyAsync(h_times, tm.ptr, sizeof(double) * nb * K, cudaMemcpyDeviceToHost, st));
-  done:;
-  }
-  cudaError_t es = cudaStreamSynchronize(st);
-  if (rc == MINSNAP_OK && es != cudaSuccess) rc = cuda_fail(es, "cudaStreamSynchronize");
-  return rc;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const int i_pos = hc.in(h_positions, sizeof(double) * nb * (K + 1) * D);
+  const int o_times = hc.out(h_times, sizeof(double) * nb * K);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_estimate_segment_times(B, K, D, hc.dev<double>(i_pos), v_max, a_max, magic, hc.dev<double>(o_times), st);
+  });
 }
-#undef TRY
+
+int minsnap_cost_sweep_host(long B, int S, int K, int D, int N, int derivative, const double* h_positions,
+                            const double* h_end_derivatives, const double* h_times, double* h_cost, int32_t* h_status) {
+  if (!shape_ok(B, K, D, N, derivative) || S < 1 || !h_positions || !h_times || !h_cost) return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const int i_pos = hc.in(h_positions, sizeof(double) * nb * (K + 1) * D);
+  const int i_end = hc.in(h_end_derivatives, sizeof(double) * nb * 2 * (N / 2 - 1) * D);
+  const int i_tm = hc.in(h_times, sizeof(double) * nb * S * K);
+  const int o_cost = hc.out(h_cost, sizeof(double) * nb * S);
+  const int o_status = hc.out(h_status, h_status ? sizeof(int32_t) * nb * S : 0);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_cost_sweep(B, S, K, D, N, derivative, hc.dev<double>(i_pos), hc.dev_if<double>(i_end, h_end_derivatives),
+                              hc.dev<double>(i_tm), hc.dev<double>(o_cost), hc.dev_if<int32_t>(o_status, h_status), st);
+  });
+}
+
+int minsnap_time_objective_host(long B, int S, int K, int D, int N, int derivative, const double* h_positions,
+                                const double* h_end_derivatives, const double* h_times, double time_penalty,
+                                double* h_objective, double* h_cost, int32_t* h_status) {
+  if (!shape_ok(B, K, D, N, derivative) || S < 1 || !h_positions || !h_times || !h_objective) return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const int i_pos = hc.in(h_positions, sizeof(double) * nb * (K + 1) * D);
+  const int i_end = hc.in(h_end_derivatives, sizeof(double) * nb * 2 * (N / 2 - 1) * D);
+  const int i_tm = hc.in(h_times, sizeof(double) * nb * S * K);
+  const int o_obj = hc.out(h_objective, sizeof(double) * nb * S);
+  const int o_cost = hc.out(h_cost, h_cost ? sizeof(double) * nb * S : 0);
+  const int o_status = hc.out(h_status, h_status ? sizeof(int32_t) * nb * S : 0);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_time_objective(B, S, K, D, N, derivative, hc.dev<double>(i_pos),
+                                  hc.dev_if<double>(i_end, h_end_derivatives), hc.dev<double>(i_tm), time_penalty,
+                                  hc.dev<double>(o_obj), hc.dev_if<double>(o_cost, h_cost),
+                                  hc.dev_if<int32_t>(o_status, h_status), st);
+  });
+}
+
+int minsnap_time_gradient_host(long B, int K, int D, int N, int derivative, const double* h_coeffs, const double* h_times,
+                               double increment, double w_d, double w_t, double* h_gradient, double* h_segment_cost) {
+  if (!shape_ok(B, K, D, N, derivative) || !(increment > 0.0) || !h_coeffs || !h_times || (!h_gradient && !h_segment_cost))
+    return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const int i_coeffs = hc.in(h_coeffs, sizeof(double) * nb * K * D * N);
+  const int i_times = hc.in(h_times, sizeof(double) * nb * K);
+  const int o_grad = hc.out(h_gradient, h_gradient ? sizeof(double) * nb * K : 0);
+  const int o_seg = hc.out(h_segment_cost, h_segment_cost ? sizeof(double) * nb * K : 0);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_time_gradient(B, K, D, N, derivative, hc.dev<double>(i_coeffs), hc.dev<double>(i_times), increment, w_d,
+                                 w_t, hc.dev_if<double>(o_grad, h_gradient), hc.dev_if<double>(o_seg, h_segment_cost), st);
+  });
+}
+
+int minsnap_collision_cost_host(long B, int K, int D, int N, const double* h_coeffs, const double* h_times,
+                                const double* h_sdf, const int32_t* h_dims, const double* h_origin, double resolution,
+                                double oob_value, const double* h_min_bound, const double* h_max_bound,
+                                int use_continuous_distance, double dt, double map_resolution, double epsilon,
+                                double robot_radius, double coll_pot_multiplier, double* h_cost, int32_t* h_is_collision,
+                                int32_t* h_charged) {
+  if (B < 0 || K < 1 || !h_dims || h_dims[0] < 1 || h_dims[1] < 1 || h_dims[2] < 1) return MINSNAP_ERR_ARG;
+  if (D != 3 || N != 10) return MINSNAP_ERR_UNSUPPORTED;
+  if (B == 0) return MINSNAP_OK;
+  if (!h_coeffs || !h_times || !h_sdf || !h_cost) return MINSNAP_ERR_ARG;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const int i_coeffs = hc.in(h_coeffs, sizeof(double) * nb * K * D * N);
+  const int i_times = hc.in(h_times, sizeof(double) * nb * K);
+  const int i_sdf = hc.in(h_sdf, sizeof(double) * (size_t)h_dims[0] * h_dims[1] * h_dims[2]);
+  const int o_cost = hc.out(h_cost, sizeof(double) * nb);
+  const int o_hit = hc.out(h_is_collision, h_is_collision ? sizeof(int32_t) * nb : 0);
+  const int o_chg = hc.out(h_charged, h_charged ? sizeof(int32_t) * nb : 0);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_collision_cost(B, K, D, N, hc.dev<double>(i_coeffs), hc.dev<double>(i_times), hc.dev<double>(i_sdf), h_dims,
+                                  h_origin, resolution, oob_value, h_min_bound, h_max_bound, use_continuous_distance, dt,
+                                  map_resolution, epsilon, robot_radius, coll_pot_multiplier, hc.dev<double>(o_cost),
+                                  hc.dev_if<int32_t>(o_hit, h_is_collision), hc.dev_if<int32_t>(o_chg, h_charged), st);
+  });
+}
 
 int minsnap_fp64_peak(int repeats, double* tflops) {
   if (!tflops || repeats < 1) return MINSNAP_ERR_ARG;

@@ -561,9 +561,10 @@ cudaError_t launch_time_gradient(long B, int K, int D, int N, int derivative, co
 
 // objective[b][s] = cost[b][s] + time_penalty (sum_k times[b][s][k])^2  (ref objectiveFunctionTime,
 // NL.i:778-784: cost_trajectory + total_time^2 * time_penalty)
+// cost and objective may be the same array (minsnap_time_objective without a separate cost buffer): no __restrict__.
 __global__ void __launch_bounds__(256) add_time_penalty_kernel(long n, int K, const double* __restrict__ times,
-                                                               const double* __restrict__ cost, double time_penalty,
-                                                               double* __restrict__ objective) {
+                                                               const double* cost, double time_penalty,
+                                                               double* objective) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double total = 0.0;

@@ -76,15 +76,32 @@ class PeerGatherBuffer:
             except Exception as exc:          # every rank must still leave the broadcast below
                 handle_bytes = [None]
                 self._owner_error = exc
+                if self.ptr:                  # the allocation succeeded but could not be exported
+                    rt.cudaFree(self.ptr)
+                    self.ptr = 0
         dist.broadcast_object_list(handle_bytes, src=dst)
         if handle_bytes[0] is None:
             raise RuntimeError("PeerGatherBuffer: rank %d could not export its buffer" % dst)
+        ok, error = 1, None
         if not self._owner:
-            handle = rt.cudaIpcMemHandle_t()
-            handle.reserved = handle_bytes[0]
-            err, ptr = rt.cudaIpcOpenMemHandle(handle, rt.cudaIpcMemLazyEnablePeerAccess)
-            self._check(err, "cudaIpcOpenMemHandle")
-            self.ptr = int(ptr)
+            try:
+                handle = rt.cudaIpcMemHandle_t()
+                handle.reserved = handle_bytes[0]
+                err, ptr = rt.cudaIpcOpenMemHandle(handle, rt.cudaIpcMemLazyEnablePeerAccess)
+                self._check(err, "cudaIpcOpenMemHandle")
+                self.ptr = int(ptr)
+            except Exception as exc:
+                ok, error = 0, exc
+        # agree on the outcome: a rank that could not map the buffer makes EVERY rank raise (nobody is left
+        # waiting in a later barrier), after the ranks that did succeed have released their mapping
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            self._views = 0
+            self.close(barrier=False)
+            raise RuntimeError("PeerGatherBuffer: rank(s) %s could not map the buffer of rank %d%s"
+                               % ([r for r, f in enumerate(flags) if not f], dst, ": %s" % error if error else ""))
+        self._views = 0
 
     @staticmethod
     def _check(err, what):
@@ -102,7 +119,13 @@ class PeerGatherBuffer:
                                         "version": 3, "strides": None}
         t = torch.as_tensor(raw, device="cuda")
         t._peer_buffer_keepalive = self
+        self._views += 1          # close() refuses to unmap while tensors over the mapping may be alive
+        import weakref
+        weakref.finalize(t, self._release_view)
         return t
+
+    def _release_view(self):
+        self._views -= 1
 
     def view(self, rank=None):
         """The block of `rank` (default: this rank) inside the peer buffer, as a CUDA tensor."""
@@ -131,6 +154,12 @@ class PeerGatherBuffer:
             self._dist.barrier()
         if not self.ptr:
             return
+        if getattr(self, "_views", 0) > 0:
+            import gc
+            gc.collect()
+            if self._views > 0:
+                raise RuntimeError("PeerGatherBuffer.close(): %d tensor(s) returned by view() / whole() are still alive; "
+                                   "drop them first (they alias the mapping that close() releases)" % self._views)
         if self._owner:
             rt.cudaFree(self.ptr)
         else:
