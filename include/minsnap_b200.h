@@ -234,6 +234,22 @@ MINSNAP_API int minsnap_time_gradient(long B, int K, int D, int N, int derivativ
                                       double increment, double w_d, double w_t, double* d_gradient,
                                       double* d_segment_cost, minsnap_stream_t stream);
 
+/* minsnap_optimize_segment_times: an additive batched driver for the time-only problem (the reference runs one
+ * NLopt instance per trajectory on the host, NL.i:230-330; NLopt is an absent third-party dependency, so no
+ * parity is claimed for the optimiser -- only for the objective and gradient it is built from).  Every
+ * trajectory descends  computeCost + time_penalty * total_time^2  along its own numeric gradient; per iteration
+ * n_steps step lengths (max_relative_step / 2^s of the step that would zero a segment time, times clamped at
+ * min_time) are evaluated by one cost sweep and the first minimum is accepted when it improves the incumbent.
+ * Five launches per iteration, all on `stream`, no host round trip.  d_times [B][K] is updated in place;
+ * d_history (optional) [iterations + 1][B] receives the incumbent objective after every iteration. */
+MINSNAP_API int minsnap_optimize_segment_times(long B, int K, int D, int N, int derivative,
+                                               const double* d_positions,
+                                               const double* d_end_derivatives, double* d_times,
+                                               int iterations, double time_penalty, int n_steps,
+                                               double max_relative_step, double min_time,
+                                               double gradient_increment, double* d_history,
+                                               minsnap_stream_t stream);
+
 /* ---- collision cost of solved trajectories against a signed-distance grid ------
  * ref: PolynomialOptimizationNonLinear::getCostAndGradientCollision (NL.i:1523-1709, cost and collision flag),
  *      getCostAndGradientPotentialESDF (NL.i:1713-1806), getDistanceSDF (NL.i:1843-1905), getCostPotential

@@ -305,26 +305,39 @@ def time_gradient(coeffs, times, increment=0.1, w_d=0.1, w_t=1.0, derivative=SNA
 
 
 def optimize_segment_times(positions, times, iterations=20, time_penalty=500.0, n_steps=16, max_relative_step=0.5,
-                           min_time=0.1, end_derivatives=None):
+                           min_time=0.1, end_derivatives=None, gradient_increment=1e-3, N=10, derivative=SNAP):
     """Additive batched driver for the time-only problem: every trajectory of the batch
-    descends objective = computeCost + time_penalty * total_time^2 along its own numeric gradient
-    (minsnap_time_gradient), with the line search done in parallel -- n_steps candidate step lengths per
-    trajectory are evaluated by one minsnap_time_objective launch and the best one (or none) is kept.
-    Everything stays on the device; the reference runs one NLopt instance per trajectory on the host.
+    descends objective = computeCost + time_penalty * total_time^2 along its own numeric gradient, the line
+    search is one cost sweep over n_steps step lengths per trajectory.  One C-ABI call
+    (minsnap_optimize_segment_times): the whole loop is enqueued on the current stream, five launches per
+    iteration, nothing returns to the host.  The reference runs one NLopt instance per trajectory on the host.
     Returns (times, objective history [iterations + 1][B])."""
     torch = _torch()
     B, K1, D = positions.shape
-    K = K1 - 1
+    times = times.clone().contiguous()
+    history = torch.empty((iterations + 1, B), dtype=torch.float64, device=positions.device)
+    capi.check(_lib().minsnap_optimize_segment_times(B, K1 - 1, D, N, derivative, _dptr(positions, torch.float64),
+                                                     _dptr(end_derivatives), _dptr(times, torch.float64), int(iterations),
+                                                     float(time_penalty), int(n_steps), float(max_relative_step),
+                                                     float(min_time), float(gradient_increment), _dptr(history), _stream()),
+               "minsnap_optimize_segment_times")
+    return times, history
+
+
+def optimize_segment_times_reference_glue(positions, times, iterations=20, time_penalty=500.0, n_steps=16,
+                                          max_relative_step=0.5, min_time=0.1, end_derivatives=None):
+    """The same descent with its glue written in elementwise torch operations around three C-ABI calls per
+    iteration (round 1's driver): kept as the checker of minsnap_optimize_segment_times in the tests."""
+    torch = _torch()
+    B, K1, D = positions.shape
     times = times.clone()
     history = [time_objective(positions, times[:, None, :].contiguous(), time_penalty, end_derivatives)[:, 0]]
-    # geometric ladder of relative step lengths: the longest moves the largest component by max_relative_step
     ladder = max_relative_step * 0.5 ** torch.arange(n_steps, dtype=torch.float64, device=positions.device)
     for _ in range(iterations):
         coeffs = solve_standard(positions, times, end_derivatives=end_derivatives, want_status=False)["coeffs"]
-        # objective gradient: d cost / dT = 0.5 dJ_d/dT (w_d = 0.5, w_t = 0) + d/dT penalty * total^2
         g = time_gradient(coeffs, times, increment=1e-3, w_d=0.5, w_t=0.0)
         g = g + 2.0 * time_penalty * times.sum(1, keepdim=True)
-        scale = (times / g.abs().clamp_min(1e-300)).min(1, keepdim=True).values   # step that would zero a time
+        scale = (times / g.abs().clamp_min(1e-300)).min(1, keepdim=True).values
         cand = times[:, None, :] - (ladder[None, :, None] * scale[:, :, None]) * g[:, None, :]
         cand = cand.clamp_min(min_time).contiguous()
         obj = time_objective(positions, cand, time_penalty, end_derivatives)

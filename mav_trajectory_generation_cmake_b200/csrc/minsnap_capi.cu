@@ -70,6 +70,11 @@ void count_mask(const uint8_t* mask, int N, int K, int* n_fixed, int* n_free) {
 void retain_pool_memory() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return;
+  // once per thread and device: the attribute call is not a capturable operation, and a caller that captures a
+  // host-API-free entry point into a CUDA graph has run it eagerly before
+  static thread_local int done_for = -1;
+  if (done_for == dev) return;
+  done_for = dev;
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
   uint64_t threshold = ~0ull;
@@ -511,6 +516,54 @@ int minsnap_time_gradient(long B, int K, int D, int N, int derivative, const dou
   CU(minsnap::launch_time_gradient(B, K, D, N, derivative, d_coeffs, d_times, increment, w_d, w_t, d_gradient,
                                    d_segment_cost, as_stream(stream)));
   return MINSNAP_OK;
+}
+
+// a batched descent on the segment times that never leaves the device.  Every iteration is five
+// launches on `stream` (solve, time gradient, step ladder, cost sweep over the ladder, select); the workspace is
+// one stream-ordered allocation.
+int minsnap_optimize_segment_times(long B, int K, int D, int N, int derivative, const double* d_positions,
+                                   const double* d_end_derivatives, double* d_times, int iterations, double time_penalty,
+                                   int n_steps, double max_relative_step, double min_time, double gradient_increment,
+                                   double* d_history, minsnap_stream_t stream) {
+  if (!shape_ok(B, K, D, N, derivative) || iterations < 0 || n_steps < 1 || !(max_relative_step > 0.0) ||
+      !(min_time > 0.0) || !(gradient_increment > 0.0))
+    return MINSNAP_ERR_ARG;
+  if (B == 0) return MINSNAP_OK;
+  if (!d_positions || !d_times) return MINSNAP_ERR_ARG;
+  if (!minsnap::standard_supported(K, D, N, derivative)) return MINSNAP_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const size_t nb = (size_t)B, S = (size_t)n_steps;
+  const size_t n_coeffs = nb * K * D * N, n_grad = nb * K, n_cand = nb * S * K, n_cost = nb * S;
+  double* ws = nullptr;
+  retain_pool_memory();
+  CU(cudaMallocAsync(reinterpret_cast<void**>(&ws), sizeof(double) * (n_coeffs + n_grad + n_cand + n_cost + nb), st));
+  double* coeffs = ws;
+  double* grad = coeffs + n_coeffs;
+  double* cand = grad + n_grad;
+  double* cost = cand + n_cand;
+  double* incumbent = cost + n_cost;
+  int rc = MINSNAP_OK;
+  // the incumbent objective at the initial times: one allocation per trajectory through the same sweep + penalty
+  rc = minsnap_time_objective(B, 1, K, D, N, derivative, d_positions, d_end_derivatives, d_times, time_penalty, incumbent,
+                              nullptr, nullptr, st);
+  if (rc == MINSNAP_OK && d_history)
+    if (cudaMemcpyAsync(d_history, incumbent, sizeof(double) * nb, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = MINSNAP_ERR_CUDA;
+  for (int it = 0; it < iterations && rc == MINSNAP_OK; ++it) {
+    rc = minsnap_solve_standard(B, K, D, N, derivative, d_positions, d_end_derivatives, d_times, 0.0, 0.0, 0.0, nullptr,
+                                coeffs, nullptr, nullptr, nullptr, st);
+    // d cost / dT = 0.5 dJ_d/dT (w_d = 0.5, w_t = 0); the penalty's gradient is added by the ladder kernel
+    if (rc == MINSNAP_OK) rc = minsnap_time_gradient(B, K, D, N, derivative, coeffs, d_times, gradient_increment, 0.5, 0.0, grad, nullptr, st);
+    cudaError_t e = cudaSuccess;
+    if (rc == MINSNAP_OK) e = minsnap::launch_time_candidates(B, n_steps, K, d_times, grad, time_penalty, max_relative_step, min_time, cand, st);
+    if (rc == MINSNAP_OK && e == cudaSuccess)
+      rc = minsnap_cost_sweep(B, n_steps, K, D, N, derivative, d_positions, d_end_derivatives, cand, cost, nullptr, st);
+    if (rc == MINSNAP_OK && e == cudaSuccess)
+      e = minsnap::launch_time_select(B, n_steps, K, cand, cost, time_penalty, d_times, incumbent,
+                                      d_history ? d_history + (size_t)(it + 1) * nb : nullptr, st);
+    if (rc == MINSNAP_OK && e != cudaSuccess) rc = cuda_fail(e, "time descent glue");
+  }
+  cudaFreeAsync(ws, st);
+  return rc;
 }
 
 // collision cost against a dense distance grid (ref NL.i:1523-1709)

@@ -580,4 +580,86 @@ cudaError_t launch_add_time_penalty(long n, int K, const double* d_times, const 
   return cudaGetLastError();
 }
 
+// =========================================================================================
+// the glue of a batched descent on the segment times, on the device.
+// One optimiser iteration = solve (coefficients at the current times) -> time gradient -> the kernel below
+// (step ladder: n_steps candidate allocations per trajectory along its own gradient) -> cost sweep over the
+// candidates -> select kernel (penalty, first minimum, accept only an improvement): 5 launches, no host
+// round trip, no temporaries beyond the workspace.
+// =========================================================================================
+// cand[b][s][k] = max(min_time, T_k - (max_relative_step / 2^s) scale_b g_k),  g = dJ/dT + 2 penalty sum(T),
+// scale_b = min_k T_k / |g_k| (the step that would zero a segment time).
+__global__ void __launch_bounds__(128) time_candidates_kernel(long B, int S, int K, const double* __restrict__ times,
+                                                              const double* __restrict__ grad_cost, double time_penalty,
+                                                              double max_relative_step, double min_time,
+                                                              double* __restrict__ cand) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * S) return;
+  const long b = idx / S;
+  const int s = (int)(idx - b * S);
+  const double* T = times + b * K;
+  const double* gc = grad_cost + b * K;
+  double total = 0.0;
+  for (int k = 0; k < K; ++k) total += T[k];
+  const double gp = 2.0 * time_penalty * total;
+  double scale = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double g = fabs(gc[k] + gp);
+    const double r = T[k] / (g < 1e-300 ? 1e-300 : g);
+    scale = k == 0 ? r : fmin(scale, r);
+  }
+  double ladder = max_relative_step;
+  for (int q = 0; q < s; ++q) ladder *= 0.5;
+  double* out = cand + idx * K;
+  for (int k = 0; k < K; ++k) {
+    const double v = T[k] - (ladder * scale) * (gc[k] + gp);
+    out[k] = v < min_time ? min_time : v;
+  }
+}
+
+// objective[b][s] = cost[b][s] + penalty (sum_k cand[b][s][k])^2; the first minimum over s replaces the
+// incumbent (times, objective) only when it is strictly smaller.  history_row (optional) receives the incumbent.
+__global__ void __launch_bounds__(128) time_select_kernel(long B, int S, int K, const double* __restrict__ cand,
+                                                          const double* __restrict__ cost, double time_penalty,
+                                                          double* __restrict__ times, double* __restrict__ incumbent,
+                                                          double* __restrict__ history_row) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double best = 0.0;
+  int arg = -1;
+  for (int s = 0; s < S; ++s) {
+    const double* c = cand + (b * S + s) * K;
+    double total = 0.0;
+    for (int k = 0; k < K; ++k) total += c[k];
+    const double obj = cost[b * S + s] + total * total * time_penalty;
+    if (arg < 0 || obj < best) { best = obj; arg = s; }
+  }
+  double cur = incumbent[b];
+  if (arg >= 0 && best < cur) {
+    const double* c = cand + (b * S + arg) * K;
+    for (int k = 0; k < K; ++k) times[b * K + k] = c[k];
+    cur = best;
+    incumbent[b] = cur;
+  }
+  if (history_row) history_row[b] = cur;
+}
+
+cudaError_t launch_time_candidates(long B, int S, int K, const double* d_times, const double* d_grad_cost,
+                                   double time_penalty, double max_relative_step, double min_time, double* d_cand,
+                                   cudaStream_t stream) {
+  if (B == 0) return cudaSuccess;
+  const long n = B * S;
+  time_candidates_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(B, S, K, d_times, d_grad_cost, time_penalty,
+                                                                         max_relative_step, min_time, d_cand);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_time_select(long B, int S, int K, const double* d_cand, const double* d_cost, double time_penalty,
+                               double* d_times, double* d_incumbent, double* d_history_row, cudaStream_t stream) {
+  if (B == 0) return cudaSuccess;
+  time_select_kernel<<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(B, S, K, d_cand, d_cost, time_penalty, d_times,
+                                                                     d_incumbent, d_history_row);
+  return cudaGetLastError();
+}
+
 }  // namespace minsnap

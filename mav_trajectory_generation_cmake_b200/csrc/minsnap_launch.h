@@ -46,6 +46,13 @@ cudaError_t launch_time_gradient(long B, int K, int D, int N, int derivative, co
 cudaError_t launch_add_time_penalty(long n, int K, const double* d_times, const double* d_cost, double time_penalty,
                                     double* d_objective, cudaStream_t stream);
 
+// device-side glue of the batched time descent
+cudaError_t launch_time_candidates(long B, int S, int K, const double* d_times, const double* d_grad_cost,
+                                   double time_penalty, double max_relative_step, double min_time, double* d_cand,
+                                   cudaStream_t stream);
+cudaError_t launch_time_select(long B, int S, int K, const double* d_cand, const double* d_cost, double time_penalty,
+                               double* d_times, double* d_incumbent, double* d_history_row, cudaStream_t stream);
+
 // ---- minsnap_standard.cu ---------------------------------------------------------------
 struct StandardSolveArgs {
   long B;

@@ -113,6 +113,52 @@ def test_batched_time_descent(ms, oracle, torch_cuda):
         assert abs(hist[-1, b] - want) <= COST_TOL * want
 
 
+def test_device_resident_descent_matches_the_glue_version(ms, oracle, torch_cuda):
+    """minsnap_optimize_segment_times (the whole loop enqueued by one C-ABI call, glue in two kernels) against the
+    same descent with its glue in elementwise torch operations: same accepted steps, same objective history; with
+    non-zero end derivatives and a graph capture of the whole optimisation."""
+    torch = torch_cuda
+    B, K, penalty = 200, 10, 0.05
+    pos, times = random_batch(oracle, B, K)
+    p, t0 = torch.from_numpy(pos).cuda(), torch.from_numpy(times).cuda()
+    end = torch.from_numpy(np.random.default_rng(3).uniform(-0.5, 0.5, (B, 2, 4, 3))).cuda()
+    for e in (None, end):
+        # One iteration: identical up to rounding (the torch glue sums the segment times pairwise, the kernel left to
+        # right like the reference).
+        t_dev, h_dev = ms.optimize_segment_times(p, t0, iterations=1, time_penalty=penalty, end_derivatives=e)
+        t_ref, h_ref = ms.api.optimize_segment_times_reference_glue(p, t0, iterations=1, time_penalty=penalty, end_derivatives=e)
+        assert h_dev.shape == h_ref.shape == (2, B)
+        assert float(((h_dev - h_ref).abs() / h_ref.abs()).max()) <= 1e-12
+        assert float((t_dev - t_ref).abs().max()) <= 1e-14 * float(t_ref.abs().max())
+        # Later iterations: the reference's central differences (h = 1e-3 on a quadratic form of size 1e3) turn a
+        # last-bit difference of the times into a 1e-7 relative difference of the gradient, so the two descents agree
+        # to that level only (measured 7e-8 after the second iteration); both never accept a worse allocation.
+        t_dev, h_dev = ms.optimize_segment_times(p, t0, iterations=10, time_penalty=penalty, end_derivatives=e)
+        t_ref, h_ref = ms.api.optimize_segment_times_reference_glue(p, t0, iterations=10, time_penalty=penalty, end_derivatives=e)
+        assert float(((h_dev - h_ref).abs() / h_ref.abs()).max()) <= 1e-4
+        assert bool((h_dev[1:] <= h_dev[:-1]).all())
+    # the loop holds no host-side decision: it can be captured into a CUDA graph and replayed
+    t_buf = t0.clone()
+    hist = torch.empty((5, B), dtype=torch.float64, device="cuda")
+    lib = ms.capi.load()
+
+    def enqueue():
+        ms.capi.check(lib.minsnap_optimize_segment_times(B, K, 3, 10, 4, ms.api._dptr(p), None, ms.api._dptr(t_buf), 4, penalty,
+                                                         16, 0.5, 0.1, 1e-3, ms.api._dptr(hist), ms.api._stream()),
+                      "minsnap_optimize_segment_times")
+    enqueue()
+    torch.cuda.synchronize()
+    first = hist.clone()
+    t_buf.copy_(t0)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        enqueue()
+    t_buf.copy_(t0)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(hist, first)
+
+
 def test_time_objective_with_soft_constraints(ms, oracle, torch_cuda):
     """ref objectiveFunctionTime with use_soft_constraints (NL.i:765-832, 2346-2426): the soft term is
     min(max_cost, exp(relative violation * weight)) per limited derivative, with the maximum of
