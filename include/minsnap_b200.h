@@ -277,6 +277,25 @@ MINSNAP_API int minsnap_collision_cost(long B, int K, int D, int N, const double
                                        double* d_cost, int32_t* d_is_collision, int32_t* d_charged,
                                        minsnap_stream_t stream);
 
+/* The same walk with the gradient of the collision cost w.r.t. the free derivatives d_p (ref
+ * getCostAndGradientCollision with gradients != NULL, NL.i:1666-1686, "paper equation (14)"): per charged sample
+ * whose speed exceeds 1e-6, axis k receives
+ *   |v| time_sum dc/dx_k (T^T L_pp)  +  time_sum c v_k / |v| (T^T V L_pp),
+ * dc/dx the central difference of the potential over +-map_resolution (getCostAndGradientPotentialESDF,
+ * NL.i:1756-1785), L = A^-1 M (NL.i:200-222).  As in the reference, the dependence of the running sums on d_p is
+ * not differentiated.  d_col_of_row [N K] = the constraint index map of minsnap_reorder (free columns are
+ * n_fixed ..), or NULL for the standard mask (n_free must then be (K-1)(N/2-1)); d_grad_free [B][n_free][3] in
+ * the layout of free_values.  d_cost, d_is_collision, d_charged as above. */
+MINSNAP_API int minsnap_collision_gradient(long B, int K, int D, int N, const double* d_coeffs,
+                                           const double* d_times, const double* d_sdf, const int32_t* h_dims,
+                                           const double* h_origin, double resolution, double oob_value,
+                                           const double* h_min_bound, const double* h_max_bound,
+                                           int use_continuous_distance, double dt, double map_resolution,
+                                           double epsilon, double robot_radius, double coll_pot_multiplier,
+                                           const int32_t* d_col_of_row, int n_fixed, int n_free,
+                                           double* d_cost, double* d_grad_free, int32_t* d_is_collision,
+                                           int32_t* d_charged, minsnap_stream_t stream);
+
 /* ---- host-buffer entry points (synchronous; copies inside) -------------------------------
  * The calls a host program makes when its data lives in host memory.  Work is cut into
  * chunks that are copied and solved on alternating streams so that PCIe and the SMs overlap.
@@ -342,6 +361,17 @@ MINSNAP_API int minsnap_collision_cost_host(long B, int K, int D, int N, const d
                                             double map_resolution, double epsilon, double robot_radius,
                                             double coll_pot_multiplier, double* h_cost,
                                             int32_t* h_is_collision, int32_t* h_charged);
+
+MINSNAP_API int minsnap_collision_gradient_host(long B, int K, int D, int N, const double* h_coeffs,
+                                                const double* h_times, const double* h_sdf,
+                                                const int32_t* h_dims, const double* h_origin,
+                                                double resolution, double oob_value,
+                                                const double* h_min_bound, const double* h_max_bound,
+                                                int use_continuous_distance, double dt,
+                                                double map_resolution, double epsilon, double robot_radius,
+                                                double coll_pot_multiplier, const int32_t* h_col_of_row,
+                                                int n_fixed, int n_free, double* h_cost, double* h_grad_free,
+                                                int32_t* h_is_collision, int32_t* h_charged);
 
 MINSNAP_API int minsnap_extrema_host(long B, int K, int D, int N, const double* h_coeffs,
                                      const double* h_times, int derivative, int mode,

@@ -373,6 +373,36 @@ def collision_cost(coeffs, times, sdf, origin, resolution, min_bound, max_bound,
     return dict(cost=cost_t, is_collision=hit, charged=charged)
 
 
+def collision_gradient(coeffs, times, sdf, origin, resolution, min_bound, max_bound, dt=0.1, map_resolution=None,
+                       epsilon=0.5, robot_radius=0.5, coll_pot_multiplier=1.0, use_continuous_distance=True, oob_value=0.0,
+                       col_of_row=None, n_fixed=0, n_free=None):
+    """Collision cost AND its gradient w.r.t. the free derivatives (ref getCostAndGradientCollision with gradients,
+    NL.i:1666-1686).  col_of_row: the int32 [N K] constraint index map on the device (minsnap_reorder) with its
+    n_fixed / n_free, or None for the standard mask.  -> dict(cost [B], gradient [B][n_free][3], is_collision [B],
+    charged [B])."""
+    torch = _torch()
+    B, K, D, N = coeffs.shape
+    if map_resolution is None:
+        map_resolution = resolution
+    if col_of_row is None:
+        n_fixed, n_free = K + N - 1, (K - 1) * (N // 2 - 1)
+    dims = np.asarray(sdf.shape, np.int32)
+    org, lo, hi = _np(origin, np.float64), _np(min_bound, np.float64), _np(max_bound, np.float64)
+    cost_t = torch.empty((B,), dtype=torch.float64, device=coeffs.device)
+    grad = torch.empty((B, n_free, 3), dtype=torch.float64, device=coeffs.device)
+    hit = torch.empty((B,), dtype=torch.int32, device=coeffs.device)
+    charged = torch.empty((B,), dtype=torch.int32, device=coeffs.device)
+    capi.check(_lib().minsnap_collision_gradient(B, K, D, N, _dptr(coeffs, torch.float64), _dptr(times, torch.float64),
+                                                 _dptr(sdf, torch.float64), _hptr(dims), _hptr(org), float(resolution),
+                                                 float(oob_value), _hptr(lo), _hptr(hi), int(bool(use_continuous_distance)),
+                                                 float(dt), float(map_resolution), float(epsilon), float(robot_radius),
+                                                 float(coll_pot_multiplier),
+                                                 _dptr(col_of_row, torch.int32) if col_of_row is not None else None,
+                                                 int(n_fixed), int(n_free), _dptr(cost_t), _dptr(grad), _dptr(hit),
+                                                 _dptr(charged), _stream()), "minsnap_collision_gradient")
+    return dict(cost=cost_t, gradient=grad, is_collision=hit, charged=charged)
+
+
 EXTREMA_OPTIMIZATION = 0   # PolynomialOptimization::computeMaximumOfMagnitude (ref LIN.i:470-503)
 EXTREMA_TRAJECTORY = 1     # Trajectory::computeMinMaxMagnitude (ref src/trajectory.cpp:181-217)
 EXTREMA_KEEP_SMALL_COEFFICIENTS = 16   # OR into mode: do not truncate coefficients below 2.2e-16
@@ -635,6 +665,33 @@ def collision_cost_host(coeffs, times, sdf, origin, resolution, min_bound, max_b
                                                   float(epsilon), float(robot_radius), float(coll_pot_multiplier),
                                                   _hptr(cost_a), _hptr(hit), _hptr(charged)), "minsnap_collision_cost_host")
     return dict(cost=cost_a, is_collision=hit, charged=charged)
+
+
+def collision_gradient_host(coeffs, times, sdf, origin, resolution, min_bound, max_bound, dt=0.1, map_resolution=None,
+                            epsilon=0.5, robot_radius=0.5, coll_pot_multiplier=1.0, use_continuous_distance=True,
+                            oob_value=0.0, col_of_row=None, n_fixed=0, n_free=None):
+    """numpy variant of collision_gradient()."""
+    coeffs, times, sdf = _np(coeffs, np.float64), _np(times, np.float64), _np(sdf, np.float64)
+    B, K, D, N = coeffs.shape
+    if map_resolution is None:
+        map_resolution = resolution
+    if col_of_row is None:
+        n_fixed, n_free = K + N - 1, (K - 1) * (N // 2 - 1)
+        col = None
+    else:
+        col = _np(col_of_row, np.int32)
+    dims = np.asarray(sdf.shape, np.int32)
+    org, lo, hi = _np(origin, np.float64), _np(min_bound, np.float64), _np(max_bound, np.float64)
+    cost_a, hit, charged = np.empty((B,), np.float64), np.empty((B,), np.int32), np.empty((B,), np.int32)
+    grad = np.empty((B, n_free, 3), np.float64)
+    capi.check(_lib().minsnap_collision_gradient_host(B, K, D, N, _hptr(coeffs), _hptr(times), _hptr(sdf), _hptr(dims),
+                                                      _hptr(org), float(resolution), float(oob_value), _hptr(lo), _hptr(hi),
+                                                      int(bool(use_continuous_distance)), float(dt), float(map_resolution),
+                                                      float(epsilon), float(robot_radius), float(coll_pot_multiplier),
+                                                      _hptr(col) if col is not None else None, int(n_fixed), int(n_free),
+                                                      _hptr(cost_a), _hptr(grad), _hptr(hit), _hptr(charged)),
+               "minsnap_collision_gradient_host")
+    return dict(cost=cost_a, gradient=grad, is_collision=hit, charged=charged)
 
 
 def save_npy(path, array):

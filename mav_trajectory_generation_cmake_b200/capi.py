@@ -50,6 +50,10 @@ SIGNATURES = {
     "minsnap_optimize_segment_times": (_i, [_l, _i, _i, _i, _i, _vp, _vp, _vp, _i, _d, _i, _d, _d, _d, _vp, _vp]),
     "minsnap_collision_cost": (_i, [_l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _i, _d, _d, _d, _d, _d, _vp, _vp,
                                     _vp, _vp]),
+    "minsnap_collision_gradient": (_i, [_l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _i, _d, _d, _d, _d, _d, _vp,
+                                        _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "minsnap_collision_gradient_host": (_i, [_l, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _i, _d, _d, _d, _d, _d,
+                                             _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "minsnap_host_alloc": (_i, [_vp, _sz]),
     "minsnap_host_free": (_i, [_vp]),
     "minsnap_reorder_host": (_i, [_i, _i, _l, _vp, _vp, _vp]),

@@ -566,19 +566,25 @@ int minsnap_optimize_segment_times(long B, int K, int D, int N, int derivative, 
   return rc;
 }
 
-// collision cost against a dense distance grid (ref NL.i:1523-1709)
-int minsnap_collision_cost(long B, int K, int D, int N, const double* d_coeffs, const double* d_times,
-                           const double* d_sdf, const int32_t* h_dims, const double* h_origin, double resolution,
-                           double oob_value, const double* h_min_bound, const double* h_max_bound,
-                           int use_continuous_distance, double dt, double map_resolution, double epsilon,
-                           double robot_radius, double coll_pot_multiplier, double* d_cost, int32_t* d_is_collision,
-                           int32_t* d_charged, minsnap_stream_t stream) {
+// collision cost and its gradient against a dense distance grid (ref NL.i:1523-1709)
+static int collision_call(long B, int K, int D, int N, const double* d_coeffs, const double* d_times,
+                          const double* d_sdf, const int32_t* h_dims, const double* h_origin, double resolution,
+                          double oob_value, const double* h_min_bound, const double* h_max_bound,
+                          int use_continuous_distance, double dt, double map_resolution, double epsilon,
+                          double robot_radius, double coll_pot_multiplier, bool want_gradient,
+                          const int32_t* d_col_of_row, int n_fixed, int n_free, double* d_cost, double* d_grad_free,
+                          int32_t* d_is_collision, int32_t* d_charged, minsnap_stream_t stream) {
   if (B < 0 || K < 1 || !h_dims || !h_origin || !h_min_bound || !h_max_bound || !(resolution > 0.0) || !(dt > 0.0) ||
       !(map_resolution > 0.0) || !(epsilon > 0.0) || h_dims[0] < 1 || h_dims[1] < 1 || h_dims[2] < 1)
     return MINSNAP_ERR_ARG;
   if (D != 3 || N != 10) return MINSNAP_ERR_UNSUPPORTED;
+  if (want_gradient) {
+    if (n_free < 0 || n_fixed < 0) return MINSNAP_ERR_ARG;
+    if (!d_col_of_row && n_free != (K - 1) * (N / 2 - 1)) return MINSNAP_ERR_ARG;   // the standard mask's count
+  }
   if (B == 0) return MINSNAP_OK;
   if (!d_coeffs || !d_times || !d_sdf || !d_cost) return MINSNAP_ERR_ARG;
+  if (want_gradient && n_free > 0 && !d_grad_free) return MINSNAP_ERR_ARG;
   minsnap::CollisionArgs a;
   a.B = B; a.K = K; a.N = N; a.d_coeffs = d_coeffs; a.d_times = d_times; a.d_sdf = d_sdf;
   a.nx = h_dims[0]; a.ny = h_dims[1]; a.nz = h_dims[2];
@@ -591,8 +597,36 @@ int minsnap_collision_cost(long B, int K, int D, int N, const double* d_coeffs, 
   a.dt = dt; a.map_resolution = map_resolution; a.epsilon = epsilon; a.robot_radius = robot_radius;
   a.coll_pot_multiplier = coll_pot_multiplier;
   a.d_cost = d_cost; a.d_is_collision = d_is_collision; a.d_charged = d_charged;
+  a.d_grad_free = (want_gradient && n_free > 0) ? d_grad_free : nullptr;
+  a.d_col_of_row = d_col_of_row; a.n_fixed = n_fixed; a.n_free = n_free;
+  if (a.d_grad_free)   // the kernel adds its segments' contributions into the free columns
+    CU(cudaMemsetAsync(d_grad_free, 0, sizeof(double) * (size_t)B * n_free * 3, as_stream(stream)));
   CU(minsnap::launch_collision_cost(a, as_stream(stream)));
   return MINSNAP_OK;
+}
+
+int minsnap_collision_cost(long B, int K, int D, int N, const double* d_coeffs, const double* d_times,
+                           const double* d_sdf, const int32_t* h_dims, const double* h_origin, double resolution,
+                           double oob_value, const double* h_min_bound, const double* h_max_bound,
+                           int use_continuous_distance, double dt, double map_resolution, double epsilon,
+                           double robot_radius, double coll_pot_multiplier, double* d_cost, int32_t* d_is_collision,
+                           int32_t* d_charged, minsnap_stream_t stream) {
+  return collision_call(B, K, D, N, d_coeffs, d_times, d_sdf, h_dims, h_origin, resolution, oob_value, h_min_bound,
+                        h_max_bound, use_continuous_distance, dt, map_resolution, epsilon, robot_radius,
+                        coll_pot_multiplier, false, nullptr, 0, 0, d_cost, nullptr, d_is_collision, d_charged, stream);
+}
+
+int minsnap_collision_gradient(long B, int K, int D, int N, const double* d_coeffs, const double* d_times,
+                               const double* d_sdf, const int32_t* h_dims, const double* h_origin, double resolution,
+                               double oob_value, const double* h_min_bound, const double* h_max_bound,
+                               int use_continuous_distance, double dt, double map_resolution, double epsilon,
+                               double robot_radius, double coll_pot_multiplier, const int32_t* d_col_of_row, int n_fixed,
+                               int n_free, double* d_cost, double* d_grad_free, int32_t* d_is_collision,
+                               int32_t* d_charged, minsnap_stream_t stream) {
+  return collision_call(B, K, D, N, d_coeffs, d_times, d_sdf, h_dims, h_origin, resolution, oob_value, h_min_bound,
+                        h_max_bound, use_continuous_distance, dt, map_resolution, epsilon, robot_radius,
+                        coll_pot_multiplier, true, d_col_of_row, n_fixed, n_free, d_cost, d_grad_free, d_is_collision,
+                        d_charged, stream);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -995,6 +1029,37 @@ int minsnap_collision_cost_host(long B, int K, int D, int N, const double* h_coe
                                   h_origin, resolution, oob_value, h_min_bound, h_max_bound, use_continuous_distance, dt,
                                   map_resolution, epsilon, robot_radius, coll_pot_multiplier, hc.dev<double>(o_cost),
                                   hc.dev_if<int32_t>(o_hit, h_is_collision), hc.dev_if<int32_t>(o_chg, h_charged), st);
+  });
+}
+
+int minsnap_collision_gradient_host(long B, int K, int D, int N, const double* h_coeffs, const double* h_times,
+                                    const double* h_sdf, const int32_t* h_dims, const double* h_origin, double resolution,
+                                    double oob_value, const double* h_min_bound, const double* h_max_bound,
+                                    int use_continuous_distance, double dt, double map_resolution, double epsilon,
+                                    double robot_radius, double coll_pot_multiplier, const int32_t* h_col_of_row,
+                                    int n_fixed, int n_free, double* h_cost, double* h_grad_free, int32_t* h_is_collision,
+                                    int32_t* h_charged) {
+  if (B < 0 || K < 1 || n_free < 0 || !h_dims || h_dims[0] < 1 || h_dims[1] < 1 || h_dims[2] < 1) return MINSNAP_ERR_ARG;
+  if (D != 3 || N != 10) return MINSNAP_ERR_UNSUPPORTED;
+  if (B == 0) return MINSNAP_OK;
+  if (!h_coeffs || !h_times || !h_sdf || !h_cost || (n_free > 0 && !h_grad_free)) return MINSNAP_ERR_ARG;
+  HostCall hc;
+  const size_t nb = (size_t)B;
+  const int i_coeffs = hc.in(h_coeffs, sizeof(double) * nb * K * D * N);
+  const int i_times = hc.in(h_times, sizeof(double) * nb * K);
+  const int i_sdf = hc.in(h_sdf, sizeof(double) * (size_t)h_dims[0] * h_dims[1] * h_dims[2]);
+  const int i_col = hc.in(h_col_of_row, h_col_of_row ? sizeof(int32_t) * (size_t)N * K : 0);
+  const int o_cost = hc.out(h_cost, sizeof(double) * nb);
+  const int o_grad = hc.out(h_grad_free, sizeof(double) * nb * n_free * 3);
+  const int o_hit = hc.out(h_is_collision, h_is_collision ? sizeof(int32_t) * nb : 0);
+  const int o_chg = hc.out(h_charged, h_charged ? sizeof(int32_t) * nb : 0);
+  return hc.run([&](cudaStream_t st) {
+    return minsnap_collision_gradient(B, K, D, N, hc.dev<double>(i_coeffs), hc.dev<double>(i_times), hc.dev<double>(i_sdf),
+                                      h_dims, h_origin, resolution, oob_value, h_min_bound, h_max_bound,
+                                      use_continuous_distance, dt, map_resolution, epsilon, robot_radius,
+                                      coll_pot_multiplier, hc.dev_if<int32_t>(i_col, h_col_of_row), n_fixed, n_free,
+                                      hc.dev<double>(o_cost), hc.dev_if<double>(o_grad, n_free > 0 ? h_grad_free : nullptr),
+                                      hc.dev_if<int32_t>(o_hit, h_is_collision), hc.dev_if<int32_t>(o_chg, h_charged), st);
   });
 }
 

@@ -90,16 +90,37 @@ __device__ __forceinline__ double cost_potential(const CollisionArgs& a, double 
   return cost;
 }
 
-// ref getCostAndGradientPotentialESDF, NL.i:1713-1753 (value)
-__device__ double potential(const CollisionArgs& a, const GridView& g, double x, double y, double z, bool* hit) {
+// ref getCostAndGradientPotentialESDF, NL.i:1713-1753 (value) and, with grad != null, NL.i:1756-1785: the central
+// difference of the potential over +-map_resolution along each axis (continuous or discrete distance as the
+// CENTRE position decides)
+__device__ double potential(const CollisionArgs& a, const GridView& g, double x, double y, double z, bool* hit,
+                            double* grad = nullptr) {
   const double inc = a.map_resolution;
   const bool valid_state = !(x < a.min_bound[0] + inc || x > a.max_bound[0] - inc || y < a.min_bound[1] + inc ||
                              y > a.max_bound[1] - inc || z < a.min_bound[2] + inc || z > a.max_bound[2] - inc);
-  const double d = (valid_state && a.use_continuous_distance) ? distance_continuous(g, x, y, z) : grid_get(g, x, y, z);
+  const bool cont = valid_state && a.use_continuous_distance;
+  const double d = cont ? distance_continuous(g, x, y, z) : grid_get(g, x, y, z);
+  if (grad) {
+    for (int k = 0; k < 3; ++k) {
+      const double ex = k == 0 ? inc : 0.0, ey = k == 1 ? inc : 0.0, ez = k == 2 ? inc : 0.0;
+      const double dl = cont ? distance_continuous(g, x - ex, y - ey, z - ez) : grid_get(g, x - ex, y - ey, z - ez);
+      const double dr = cont ? distance_continuous(g, x + ex, y + ey, z + ez) : grid_get(g, x + ex, y + ey, z + ez);
+      bool h;
+      const double cl = cost_potential(a, dl, &h), cr = cost_potential(a, dr, &h);
+      grad[k] = (cr - cl) / (2.0 * inc);
+    }
+  }
   return cost_potential(a, d, hit);
 }
 
-template <int N>
+// kGrad adds the gradient w.r.t. the free derivatives (NL.i:1666-1686).  The reference adds, per charged sample,
+//   |v| time_sum dc/dx_k (T^T L_pp) + time_sum c v_k / |v| (T^T V L_pp)      to axis k's gradient,
+// two row vectors through L = A^-1 M per sample.  Both are linear in the sample's monomial vector, so the lanes
+// accumulate in COEFFICIENT space instead -- gc[k][n] += alpha_k t^n + beta_k n t^(n-1), 20 FMAs per axis -- and
+// once per segment the warp folds the 3 x N sums and applies A^-T in closed form
+// (A^-1_T[n][r] = A1inv[n][r] T^(k_r - n)): row r of the segment's end-point constraints receives
+// T^(k_r) sum_n A1inv[n][r] T^-n gc[k][n] and adds it to its free column.  Same sum, reassociated.
+template <int N, bool kGrad>
 __global__ void __launch_bounds__(128) collision_cost_kernel(CollisionArgs a) {
   const int lane = threadIdx.x & 31;
   const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
@@ -127,6 +148,13 @@ __global__ void __launch_bounds__(128) collision_cost_kernel(CollisionArgs a) {
         for (int n = 0; n < N; ++n) c[k][n] = __ldg(cb + ((long)i * 3 + k) * N + n);
 #pragma unroll
         for (int n = 0; n + 1 < N; ++n) dc[k][n] = (n + 1) * c[k][n + 1];
+      }
+      double gc[kGrad ? 3 : 1][kGrad ? N : 1];   // this lane's share of dJ/dcoefficients of segment i
+      if (kGrad) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int n = 0; n < N; ++n) gc[k][n] = 0.0;
       }
       double t0 = 0.0, t_end = 0.0;
       while (true) {
@@ -178,10 +206,29 @@ __global__ void __launch_bounds__(128) collision_cost_kernel(CollisionArgs a) {
         }
         if (mine) {
           bool hit;
-          const double cp = potential(a, g, x, y, z, &hit);
+          double gp[3];
+          const double cp = potential(a, g, x, y, z, &hit, kGrad ? gp : nullptr);
           collided |= hit;
-          J += cp * sqrt(vx * vx + vy * vy + vz * vz) * my_ts;
+          const double vnorm = sqrt(vx * vx + vy * vy + vz * vz);
+          J += cp * vnorm * my_ts;
           ++charged;
+          if (kGrad && vnorm > 1e-6) {   // ref NL.i:1668: slower samples keep their cost and drop their gradient
+            const double v3[3] = {vx, vy, vz};
+            double alpha[3], beta[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              alpha[k] = vnorm * my_ts * gp[k];
+              beta[k] = my_ts * cp * v3[k] / vnorm;
+            }
+            double tp = 1.0, tm = 0.0;   // t^n and n t^(n-1)
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) gc[k][n] = fma(alpha[k], tp, fma(beta[k], tm, gc[k][n]));
+              tm = (n + 1) * tp;
+              tp *= t;
+            }
+          }
         }
         if (n_valid < 32) {
           t_end = __shfl_sync(0xffffffffu, t, n_valid);   // the loop variable when the reference's loop ends
@@ -190,6 +237,48 @@ __global__ void __launch_bounds__(128) collision_cost_kernel(CollisionArgs a) {
         t0 = __shfl_sync(0xffffffffu, t, 31) + dt;
       }
       time_sum += -dt + (T - t_end);   // ref NL.i:1698: make sure the dt is correct for the next segment
+      if (kGrad) {
+        // fold the lanes' sums (fixed-order butterfly), then lanes 3 r + k map row r, axis k through A^-T
+        const double iT = 1.0 / T;
+        double s[3][N];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double ip = 1.0;
+#pragma unroll
+          for (int n = 0; n < N; ++n) {
+            double v = gc[k][n];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            s[k][n] = v * ip;   // T^-n gc[k][n]
+            ip *= iT;
+          }
+        }
+        __syncwarp();   // the previous segment's additions to shared columns are visible
+        if (lane < 3 * N) {
+          const int r = lane / 3, k = lane - 3 * r;
+          const int order = r % (N / 2);
+          int col;
+          if (a.d_col_of_row) {
+            col = a.d_col_of_row[i * N + r] - a.n_fixed;
+          } else {   // standard mask: interior vertices free in derivatives 1 .. N/2-1
+            const int vertex = i + (r >= N / 2 ? 1 : 0);
+            col = (order >= 1 && vertex >= 1 && vertex <= K - 1) ? (vertex - 1) * (N / 2 - 1) + (order - 1) : -1;
+          }
+          if (col >= 0 && col < a.n_free) {
+            double acc = 0.0;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+              const double sk = k == 0 ? s[0][n] : (k == 1 ? s[1][n] : s[2][n]);
+              acc = fma(minsnap_tables::kA1inv_N10[n * N + r], sk, acc);
+            }
+            double tk = 1.0;
+            for (int e = 0; e < order; ++e) tk *= T;
+            double* dst = a.d_grad_free + (b * (long)a.n_free + col) * 3 + k;
+            *dst += acc * tk;
+          }
+        }
+        __syncwarp();
+      }
     }
     // fixed-order butterfly: the sum does not depend on timing
 #pragma unroll
@@ -216,7 +305,10 @@ cudaError_t launch_collision_cost(const CollisionArgs& a, cudaStream_t stream) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (grid > (long)sms * 32) grid = (long)sms * 32;
-  collision_cost_kernel<10><<<(int)grid, threads, 0, stream>>>(a);
+  if (a.d_grad_free)
+    collision_cost_kernel<10, true><<<(int)grid, threads, 0, stream>>>(a);
+  else
+    collision_cost_kernel<10, false><<<(int)grid, threads, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -138,6 +138,10 @@ struct CollisionArgs {
   double* d_cost;           // [B]
   int32_t* d_is_collision;  // optional [B]
   int32_t* d_charged;       // optional [B]: number of samples that were charged
+  // gradient w.r.t. the free derivatives (NL.i:1666-1686); all unused when d_grad_free is null
+  double* d_grad_free;          // [B][n_free][3], ZERO on entry
+  const int32_t* d_col_of_row;  // [N K] constraint index map, or null = the standard mask
+  int n_fixed, n_free;
 };
 cudaError_t launch_collision_cost(const CollisionArgs& a, cudaStream_t stream);
 

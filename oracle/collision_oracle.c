@@ -193,3 +193,94 @@ API double orc_collision_cost(int N, int K, const double* coeffs, const double* 
   if (n_charged) *n_charged = charged;
   return J_c;
 }
+
+/* NL.i:1523-1709 getCostAndGradientCollision with gradients != NULL: the cost as above plus, per charged sample
+ * whose speed exceeds 1e-6 (NL.i:1668; slower samples are charged but their gradient is dropped), for every axis k
+ *   grad_c[k] += ( |v| time_sum dc/dx_k  T_all^T L_pp  +  time_sum c v_k / |v|  T_all^T V_all L_pp )^T      (NL.i:1672-1679)
+ * dc/dx the central difference of the potential over +-map_resolution (getCostAndGradientPotentialESDF,
+ * NL.i:1756-1785), L = A^-1 M the map from [d_f; d_p] to the coefficients (NL.i:200-222), L_pp its free columns,
+ * V the derivative matrix (V[n][n+1] = n + 1).  The caller passes the per-segment A^-1 [K][N][N] (the oracle's own
+ * invertMappingMatrix) and the reference's constraint index map; L_pp and V_all L_pp are formed densely once, as
+ * the reference holds them, and every sample takes its row-vector products with the rows of its segment (the
+ * other entries of T_all are zero).  grad [n_free][3]. */
+API double orc_collision_cost_gradient(int N, int K, const double* coeffs, const double* times, const double* ainv,
+                                       const int32_t* col_of_row, int n_fixed, int n_free, const double* data, int nx,
+                                       int ny, int nz, const double* origin, double resolution, double oob_value,
+                                       const double* min_bound, const double* max_bound, int use_continuous_distance,
+                                       double dt, double map_resolution, double epsilon, double robot_radius,
+                                       double coll_pot_multiplier, double* Lpp /* scratch [K N][n_free] */,
+                                       double* VLpp /* scratch [K N][n_free] */, double* grad, int* is_collision,
+                                       int* n_charged) {
+  Grid g = {data, nx, ny, nz, {origin[0], origin[1], origin[2]}, resolution, oob_value};
+  PotentialParams pp = {{min_bound[0], min_bound[1], min_bound[2]}, {max_bound[0], max_bound[1], max_bound[2]},
+                        use_continuous_distance, map_resolution, epsilon, robot_radius, coll_pot_multiplier};
+  /* L_pp = (A^-1 M)[:, free]: M maps compact column col_of_row[i N + r] onto row r of segment i */
+  for (size_t e = 0; e < (size_t)K * N * n_free; ++e) Lpp[e] = VLpp[e] = 0.0;
+  for (int i = 0; i < K; ++i)
+    for (int r = 0; r < N; ++r) {
+      const int col = col_of_row[i * N + r] - n_fixed;
+      if (col < 0) continue;
+      for (int n = 0; n < N; ++n) Lpp[((size_t)i * N + n) * n_free + col] += ainv[((size_t)i * N + n) * N + r];
+    }
+  for (int i = 0; i < K; ++i)
+    for (int n = 0; n + 1 < N; ++n)
+      for (int col = 0; col < n_free; ++col)
+        VLpp[((size_t)i * N + n) * n_free + col] = (n + 1) * Lpp[((size_t)i * N + n + 1) * n_free + col];
+  for (int e = 0; e < n_free * 3; ++e) grad[e] = 0.0;
+
+  double J_c = 0.0;
+  int any_collision = 0, charged = 0;
+  double prev[3] = {0.0, 0.0, 0.0};
+  double time_sum = -1.0, dist_sum = 0.0, t = 0.0;
+  for (int i = 0; i < K; ++i) {
+    for (t = 0.0; t < times[i]; t += dt) {
+      double Tv[32];
+      for (int n = 0; n < N; ++n) Tv[n] = pow(t, n);
+      double pos[3], vel[3];
+      for (int k = 0; k < 3; ++k) {
+        const double* c = coeffs + ((size_t)i * 3 + k) * N;
+        double p = 0.0, v = 0.0;
+        for (int n = 0; n < N; ++n) p += Tv[n] * c[n];
+        for (int n = 0; n + 1 < N; ++n) v += Tv[n] * ((n + 1) * c[n + 1]);
+        pos[k] = p;
+        vel[k] = v;
+      }
+      if (time_sum < 0) {
+        time_sum = 0.0;
+        prev[0] = pos[0]; prev[1] = pos[1]; prev[2] = pos[2];
+        continue;
+      }
+      time_sum += dt;
+      {
+        const double dx = pos[0] - prev[0], dy = pos[1] - prev[1], dz = pos[2] - prev[2];
+        dist_sum += sqrt(dx * dx + dy * dy + dz * dz);
+      }
+      prev[0] = pos[0]; prev[1] = pos[1]; prev[2] = pos[2];
+      if (dist_sum < map_resolution) continue;
+      int hit;
+      double gpot[3];
+      const double c = potential(&g, &pp, pos, gpot, &hit);
+      if (hit) any_collision = 1;
+      const double vnorm = sqrt(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+      J_c += c * vnorm * time_sum;
+      ++charged;
+      if (vnorm > 1e-6) {
+        for (int col = 0; col < n_free; ++col) {
+          double tl = 0.0, tvl = 0.0;   /* T_all^T L_pp and T_all^T V_all L_pp, column col */
+          for (int n = 0; n < N; ++n) {
+            tl += Tv[n] * Lpp[((size_t)i * N + n) * n_free + col];
+            tvl += Tv[n] * VLpp[((size_t)i * N + n) * n_free + col];
+          }
+          for (int k = 0; k < 3; ++k)
+            grad[col * 3 + k] += vnorm * time_sum * gpot[k] * tl + time_sum * c * vel[k] / vnorm * tvl;
+        }
+      }
+      dist_sum = 0.0;
+      time_sum = 0.0;
+    }
+    time_sum += -dt + (times[i] - t);
+  }
+  if (is_collision) *is_collision = any_collision;
+  if (n_charged) *n_charged = charged;
+  return J_c;
+}

@@ -299,6 +299,39 @@ def collision_cost(coeffs, times, sdf, origin, resolution, min_bound, max_bound,
     return cost, hit.value, charged.value
 
 
+def collision_cost_gradient(coeffs, times, col_of_row, n_fixed, n_free, sdf, origin, resolution, min_bound, max_bound,
+                            dt=0.1, map_resolution=None, epsilon=0.5, robot_radius=0.5, coll_pot_multiplier=1.0,
+                            use_continuous_distance=True, oob_value=0.0):
+    """oracle/collision_oracle.c: ref getCostAndGradientCollision with gradients (NL.i:1523-1709), one trajectory.
+    coeffs [K][3][N], times [K], col_of_row [K N] (the reference's constraint index map) ->
+    (cost, grad [n_free][3] w.r.t. the free derivatives, is_collision, n_charged)."""
+    build()
+    lib = C.CDLL(os.path.join(_LIBDIR, "liboracle_f64.so"))
+    lib.orc_collision_cost_gradient.restype = C.c_double
+    d = lambda a: np.ascontiguousarray(np.asarray(a, np.float64))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    c, t, g = d(coeffs), d(times), d(sdf)
+    K, D, N = c.shape
+    assert D == 3
+    orc = Oracle("f64")
+    ainv = np.stack([orc.invert_mapping_matrix(orc.mapping_matrix(N, float(T))) for T in t])
+    ainv = d(ainv)
+    cr = np.ascontiguousarray(np.asarray(col_of_row, np.int32))
+    org, lo, hi = d(origin), d(min_bound), d(max_bound)
+    if map_resolution is None:
+        map_resolution = resolution
+    grad = np.zeros((n_free, 3))
+    s1, s2 = np.zeros((K * N, max(n_free, 1))), np.zeros((K * N, max(n_free, 1)))
+    hit, charged = C.c_int(), C.c_int()
+    cost = lib.orc_collision_cost_gradient(N, K, p(c), p(t), p(ainv), p(cr), int(n_fixed), int(n_free), p(g), g.shape[0],
+                                           g.shape[1], g.shape[2], p(org), C.c_double(resolution), C.c_double(oob_value),
+                                           p(lo), p(hi), int(bool(use_continuous_distance)), C.c_double(dt),
+                                           C.c_double(map_resolution), C.c_double(epsilon), C.c_double(robot_radius),
+                                           C.c_double(coll_pot_multiplier), p(s1), p(s2), p(grad), C.byref(hit),
+                                           C.byref(charged))
+    return cost, grad, hit.value, charged.value
+
+
 def collision_potential(position, sdf, origin, resolution, min_bound, max_bound, map_resolution=None, epsilon=0.5,
                         robot_radius=0.5, coll_pot_multiplier=1.0, use_continuous_distance=True, oob_value=0.0):
     """ref getCostAndGradientPotentialESDF (NL.i:1713-1806): (cost, numeric gradient [3], is_collision)."""
