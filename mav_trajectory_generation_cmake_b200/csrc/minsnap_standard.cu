@@ -14,6 +14,7 @@
 #include "minsnap_standard_fast.cuh"
 #include "minsnap_standard_bcr.cuh"
 #include "minsnap_standard_tm.cuh"
+#include "minsnap_standard_chunked.cuh"
 
 namespace minsnap {
 
@@ -164,8 +165,34 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
     // 0.48 ms for 4,096, and keeps that time up to ~19,000 trajectories (16 per warp, 8 warps per
     // SM).  MINSNAP_LONG_CHAIN_KERNEL=pair|bcr forces one.
     const char* which = a.K > fast::kMaxK ? std::getenv("MINSNAP_LONG_CHAIN_KERNEL") : nullptr;
-    const int forced = !which ? 0 : std::strcmp(which, "pair") == 0 ? 1 : std::strcmp(which, "bcr") == 0 ? 2 : 0;
+    const int forced = !which ? 0 : std::strcmp(which, "pair") == 0 ? 1 : std::strcmp(which, "bcr") == 0 ? 2
+                                  : std::strcmp(which, "chunked") == 0 ? 3 : 0;
     const bool small_batch = a.B <= 148L * 2 * 19;
+    // Partitioned route (minsnap_standard_chunked.cuh): chunk Schur complements, separator solve, then every chunk
+    // through the headline kernel.  Its four launches cost ~70 us however small the batch; the reduction kernel's
+    // ceil(B / 296) x 25 us is below that up to four waves (K = 256: 1,024 -> 0.100 against 0.107 ms, 4,096 ->
+    // 0.348 against 0.267 ms, 16,384 -> 1.35 against 0.93 ms).  MINSNAP_LONG_CHAIN_KERNEL=chunked forces it.
+    const bool chunk_ok = chunked::supported(a.K, a.D, a.N, a.derivative) && p.aligned16 &&
+                          reinterpret_cast<uintptr_t>(a.d_coeffs) % 16 == 0;
+    if (chunk_ok && (forced == 3 || (forced == 0 && a.B > 148L * 2 * 4))) {
+      double* cost = p.cost;
+      p.cost = nullptr;
+      if (!p.times) {
+        double* dst = p.times_out;
+        if (!dst) {
+          if ((e = times_scratch.alloc(sizeof(double) * (size_t)a.B * a.K, stream)) != cudaSuccess) return e;
+          dst = static_cast<double*>(times_scratch.ptr);
+        }
+        if ((e = launch_estimate_times(a.B, a.K, a.D, a.d_positions, a.v_max, a.a_max, a.magic, dst, stream)) != cudaSuccess)
+          return e;
+        p.times = dst;
+      }
+      e = chunked::launch(p, a.D, stream);
+      if (e == cudaSuccess && cost) return launch_cost(a.B, a.K, a.D, a.N, a.derivative, a.d_coeffs, p.times, cost, stream);
+      if (e != cudaErrorNotSupported) return e;
+      p.cost = cost;   // no tensor map: the older routes below
+      p.times = a.d_times;
+    }
     if (bcr_ok && (!fast_ok || (forced != 1 && (small_batch || forced == 2)))) {
       double* cost = p.cost;
       p.cost = nullptr;

@@ -217,6 +217,10 @@ struct FastParams {
   int sweep_S;  // > 0: cost-only time sweep, times is [B][S][K]
   bool aligned16;  // positions / times pointers are 16-byte aligned (16-byte cp.async allowed)
   double* slot_scratch = nullptr;  // long chains: [warp][slot][lane] block storage in global memory
+  // > 0 (headline kernel only): the problems are the chunks of longer trajectories, chunk_J per trajectory, and
+  // `positions` is the trajectories' own array [B / chunk_J][chunk_J K + 1][D]: problem t reads its K + 1
+  // vertices from vertex t K + t / chunk_J on (consecutive chunks share a vertex)
+  int chunk_J = 0;
 };
 
 template <int D>

@@ -226,7 +226,20 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   // inputs by cp.async: every chunk of a batch in flight before the single wait
   auto issue_inputs = [&](long b0) {
     const int n = (int)min((long)kPairsPerWarp, p.B - b0);
-    fast::async_copy_doubles(pos_s, p.positions + b0 * per_pos, n * per_pos, lane, p.aligned16);
+    if (p.chunk_J > 0) {
+      // chunks of longer trajectories: every problem's vertices from its own place in the trajectories' array
+      long t = b0;
+      long traj = t / p.chunk_J;
+      int in_traj = (int)(t - traj * p.chunk_J);
+      for (int r = 0; r < n; ++r) {
+        const double* src = p.positions + (t * K + traj) * D;
+        for (int o = lane; o < per_pos; o += kWarp) __pipeline_memcpy_async(pos_s + r * per_pos + o, src + o, 8);
+        ++t;
+        if (++in_traj == p.chunk_J) { in_traj = 0; ++traj; }
+      }
+    } else {
+      fast::async_copy_doubles(pos_s, p.positions + b0 * per_pos, n * per_pos, lane, p.aligned16);
+    }
     if (p.times) fast::async_copy_doubles(time_s, p.times + b0 * K, n * K, lane, p.aligned16);
     __pipeline_commit();
   };
@@ -264,7 +277,7 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
     rec_tab[sd][o] = v;
   }
   if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&coeff_map)) : "memory");
-  if (!pdl && lane == 0 && p.aligned16) {
+  if (!pdl && lane == 0 && p.aligned16 && p.chunk_J == 0) {
     const long pf = base + (long)resident_warps * kPairsPerWarp;
     if (pf + kPairsPerWarp <= p.B) {
       bulk_prefetch_l2(p.positions + pf * per_pos, (uint32_t)(kPairsPerWarp * per_pos * sizeof(double)));
@@ -282,7 +295,7 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   if (pdl) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (base < p.B) issue_inputs(base);
-    if (lane == 0 && p.aligned16) {
+    if (lane == 0 && p.aligned16 && p.chunk_J == 0) {
       const long pf = base + (long)resident_warps * kPairsPerWarp;
       if (pf + kPairsPerWarp <= p.B) {
         bulk_prefetch_l2(p.positions + pf * per_pos, (uint32_t)(kPairsPerWarp * per_pos * sizeof(double)));

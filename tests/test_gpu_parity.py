@@ -316,6 +316,48 @@ def test_long_chain_kernels_agree(ms, oracle, torch_cuda, monkeypatch, D):
         assert check_path(out["coeffs"].cpu().numpy()[0], times[0], mask, values[0], oracle) < 1e-6
 
 
+@pytest.mark.parametrize("D", [1, 2, 3])
+def test_long_chain_partitioned_route(ms, oracle, torch_cuda, monkeypatch, D):
+    """The partitioned route (chunk Schur complements, separator solve, every chunk through the headline kernel;
+    minsnap_standard_chunked.cuh) against the cyclic-reduction kernel on every chain length it takes -- K a multiple
+    of an even chunk length <= 12 with an even number of chunks -- with non-zero boundary derivatives, device-side
+    segment times and all optional outputs, ragged batches included; and against the oracle at K = 256."""
+    torch = torch_cuda
+    rng = np.random.default_rng(77 + D)
+    for K, B in ((32, 5), (40, 3), (48, 17), (64, 33), (96, 2), (120, 1), (128, 40), (192, 7), (256, 19), (384, 4), (512 if D < 3 else 480, 3)):
+        pos = np.cumsum(rng.uniform(0.3, 2.0, (B, K + 1, D)) * rng.choice([-1.0, 1.0], (B, K + 1, D)), axis=1)
+        ends = rng.normal(size=(B, 2, 4, D))
+        outs = {}
+        for which in ("bcr", "chunked"):
+            monkeypatch.setenv("MINSNAP_LONG_CHAIN_KERNEL", which)
+            outs[which] = ms.solve_standard(dev(torch, pos), None, end_derivatives=dev(torch, ends), v_max=3.0,
+                                            a_max=5.0, want_free=True, want_cost=True, want_times=True)
+        a, b = outs["bcr"], outs["chunked"]
+        assert (a["status"] == 0).all() and (b["status"] == 0).all(), K
+        # the partitioned route runs the stand-alone estimateSegmentTimes kernel, the reduction kernel its own copy
+        assert float((a["times"] / b["times"] - 1.0).abs().max()) <= 1e-14
+        assert coeff_rel_err(a["coeffs"].cpu().numpy(), b["coeffs"].cpu().numpy()) <= 1e-9, K
+        scale = a["free_values"].abs().amax(dim=(1, 2), keepdim=True)
+        assert float(((a["free_values"] - b["free_values"]).abs() / scale).max()) <= 1e-9, K
+        assert float((a["cost"] / b["cost"] - 1.0).abs().max()) <= 1e-9, K
+    # against the oracle, rest-to-rest, given times, K = 256 (BASELINE config 4's shape)
+    monkeypatch.setenv("MINSNAP_LONG_CHAIN_KERNEL", "chunked")
+    K = 256
+    pos, times = random_batch(oracle, 2, K, D=D)
+    out = ms.solve_standard(dev(torch, pos), dev(torch, times), want_cost=True)
+    ref = oracle_solve_batch(oracle, standard_mask(K), batch_values(pos), times)
+    assert (out["status"] == 0).all()
+    assert coeff_rel_err(out["coeffs"].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
+    assert np.abs(out["cost"].cpu().numpy() / ref["cost"] - 1.0).max() <= COST_TOL
+    # a non-positive segment time inside a chunk is reported for its trajectory only
+    bad = times.copy()
+    bad[1, 100] = -1.0
+    out = ms.solve_standard(dev(torch, pos), dev(torch, bad))
+    st = out["status"].cpu().numpy()
+    assert st[0] == 0 and (st[1] & 2)
+    monkeypatch.delenv("MINSNAP_LONG_CHAIN_KERNEL")
+
+
 def test_long_chain_status_bits(ms, oracle, torch_cuda):
     torch = torch_cuda
     K, B = 64, 4
