@@ -15,6 +15,9 @@
 // __constant__: kernels that index the tables with compile-time constants get c[bank][offset]
 // operands straight into DFMA/DMUL (no loads, no immediate moves)
 #define MINSNAP_TABLE_QUAL static __constant__
+// tables a kernel reads with a per-lane index live in global memory (coalesced; a lane-indexed read of a
+// __constant__ array is replayed once per distinct address)
+#define MINSNAP_TABLE_GLOBAL_QUAL static __device__
 #include "minsnap_tables.h"
 
 namespace minsnap {

@@ -208,7 +208,9 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   //   rec_tab[side][49 + a]          = side ? (-1)^(a+1) A1inv[1+a][1+a] : 0             (c_k from old_k)
   __shared__ __align__(16) double rec_tab[2][kRecTab];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  // through a shuffle the compiler knows the warp index is warp-uniform: addresses and batch bases derived from
+  // it stay in uniform registers, and the TMA operands need no per-lane vote loop
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int K = p.K;
   const int per_pos = (K + 1) * D;
   constexpr int kVec = kF * D;    // doubles per vertex vector
@@ -253,29 +255,8 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   // 46.5 us per 65,536 solves.  Without pdl the first batch's loads are in flight during the allocation.
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (!pdl && base < p.B) issue_inputs(base);
-  for (int e = threadIdx.x; e < 2 * kRecTab; e += blockDim.x) {
-    const int sd = e / kRecTab, o = e - sd * kRecTab;
-    double v = 0.0;
-    if (o < 45) {
-      const int i = 5 + o / 9, c = o % 9;
-      if (c == 0) v = minsnap_tables::kA1inv_N10[i * 10 + 5];
-      else {
-        const int a = (c - 1) & 3;
-        const bool newer = c <= 4;
-        const int col = (newer != (sd != 0)) ? 1 + a : 6 + a;   // the start vector's column, or the end vector's
-        v = minsnap_tables::kA1inv_N10[i * 10 + col];
-        if (sd && !(a & 1)) v = -v;   // derivative k = a + 1 odd
-      }
-    } else if (o < 53) {
-      const int a = (o - 45) & 3;
-      const bool newer = o < 49;
-      if (newer != (sd != 0)) {   // the vector that starts the segment
-        v = minsnap_tables::kA1inv_N10[(1 + a) * 10 + (1 + a)];
-        if (sd && !(a & 1)) v = -v;
-      }
-    }
-    rec_tab[sd][o] = v;
-  }
+  // the table is generated (tools/gen_tables.py) and read from global memory, one coalesced load per CTA
+  for (int e = threadIdx.x; e < 2 * kRecTab; e += blockDim.x) (&rec_tab[0][0])[e] = minsnap_tables::kRecoveryRoles_N10[e];
   if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&coeff_map)) : "memory");
   if (!pdl && lane == 0 && p.aligned16 && p.chunk_J == 0) {
     const long pf = base + (long)resident_warps * kPairsPerWarp;
