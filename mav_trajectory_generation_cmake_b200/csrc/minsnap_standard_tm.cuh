@@ -228,7 +228,7 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   // inputs by cp.async: every chunk of a batch in flight before the single wait
   auto issue_inputs = [&](long b0) {
     const int n = (int)min((long)kPairsPerWarp, p.B - b0);
-    if (p.chunk_J > 0) {
+    if (kExtras && p.chunk_J > 0) {
       // chunks of longer trajectories: every problem's vertices from its own place in the trajectories' array
       long t = b0;
       long traj = t / p.chunk_J;
@@ -245,44 +245,37 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
     if (p.times) fast::async_copy_doubles(time_s, p.times + b0 * K, n * K, lane, p.aligned16);
     __pipeline_commit();
   };
-  // The first batch's loads are in flight while the CTA allocates its tensor memory; the batch that will
-  // take this warp's place on the SM one wave from now is pulled into L2 (TMA prefetch), so that only the
-  // first wave of a launch waits for DRAM.
   // Programmatic dependent launch (pdl): the next launch on the stream may start filling the SMs this
   // launch's last CTAs leave, and runs its prologue (recovery table, tensor-memory allocation) there; it reads
   // nothing a predecessor may have written before griddepcontrol.wait, which returns once the predecessor has
   // completed and flushed -- stream order as the caller sees it is unchanged.  Back-to-back launches: 49.3 ->
   // 46.5 us per 65,536 solves.  Without pdl the first batch's loads are in flight during the allocation.
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (!pdl && base < p.B) issue_inputs(base);
-  // the table is generated (tools/gen_tables.py) and read from global memory, one coalesced load per CTA
-  for (int e = threadIdx.x; e < 2 * kRecTab; e += blockDim.x) (&rec_tab[0][0])[e] = minsnap_tables::kRecoveryRoles_N10[e];
+  // the recovery table is generated (tools/gen_tables.py) and arrives from global memory by cp.async: nobody
+  // waits for it before the first batch's inputs are waited for
+  for (int e = threadIdx.x; e < 2 * kRecTab; e += blockDim.x)
+    __pipeline_memcpy_async(&rec_tab[0][0] + e, minsnap_tables::kRecoveryRoles_N10 + e, 8);
+  __pipeline_commit();
   if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&coeff_map)) : "memory");
-  if (!pdl && lane == 0 && p.aligned16 && p.chunk_J == 0) {
-    const long pf = base + (long)resident_warps * kPairsPerWarp;
-    if (pf + kPairsPerWarp <= p.B) {
-      bulk_prefetch_l2(p.positions + pf * per_pos, (uint32_t)(kPairsPerWarp * per_pos * sizeof(double)));
-      if (p.times) bulk_prefetch_l2(p.times + pf * K, (uint32_t)(kPairsPerWarp * K * sizeof(double)));
-    }
-  }
-
-  // tensor memory: one allocation per CTA, every warp works in its own lane quarter
-  if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)tmem_cols);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_base_slot;
-  const uint32_t taddr = tmem_base + ((uint32_t)(warp & 3) << 21);   // lane field (bits 31..16) = 32 (warp % 4)
+  // tensor memory: one allocation per CTA (warp 0), every warp works in its own lane quarter.  The warps meet
+  // the allocation at a barrier BEFORE any of them waits for its inputs (a barrier one block into the sweep,
+  // with the arithmetic under way, was measured 1.4 us slower per 65,536 solves).
+  uint32_t taddr = 0;
+  bool tmem_ready = false;
+  auto tmem_meet = [&](bool inputs_in_flight) {
+    // this thread's part of the recovery table has landed (the inputs, committed after it, may still be in flight)
+    if (inputs_in_flight) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    taddr = tmem_base_slot + ((uint32_t)(warp & 3) << 21);   // lane field (bits 31..16) = 32 (warp % 4)
+    tmem_ready = true;
+  };
   if (pdl) {
+    // all of this runs while the predecessor's last CTAs drain
+    if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)tmem_cols);
+    tmem_meet(false);
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (base < p.B) issue_inputs(base);
-    if (lane == 0 && p.aligned16 && p.chunk_J == 0) {
-      const long pf = base + (long)resident_warps * kPairsPerWarp;
-      if (pf + kPairsPerWarp <= p.B) {
-        bulk_prefetch_l2(p.positions + pf * per_pos, (uint32_t)(kPairsPerWarp * per_pos * sizeof(double)));
-        if (p.times) bulk_prefetch_l2(p.times + pf * K, (uint32_t)(kPairsPerWarp * K * sizeof(double)));
-      }
-    }
   }
 
   const int side = lane >> 4;   // 0: top-down lane, 1: bottom-up lane
@@ -292,10 +285,29 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   const double flip[kF] = {side ? -1.0 : 1.0, 1.0, side ? -1.0 : 1.0, 1.0};   // (-1)^k, k = 1..4, bottom-up lane
 
   int buf = 0;
+  bool first = true;
   for (; base < p.B; base += stride) {
     const int n_here = (int)min((long)kPairsPerWarp, p.B - base);
     const long prob = base + q;
     const bool active = q < n_here;
+    __syncwarp();   // every lane is done with the previous batch's inputs
+    issue_inputs(base);
+    if (first) {
+      first = false;
+      // the batch that will take this warp's place on the SM one wave from now is pulled into L2 (TMA
+      // prefetch), so that only the first wave of a launch waits for DRAM
+      if (lane == 0 && p.aligned16 && !(kExtras && p.chunk_J > 0)) {
+        const long pf = base + (long)resident_warps * kPairsPerWarp;
+        if (pf + kPairsPerWarp <= p.B) {
+          bulk_prefetch_l2(p.positions + pf * per_pos, (uint32_t)(kPairsPerWarp * per_pos * sizeof(double)));
+          if (p.times) bulk_prefetch_l2(p.times + pf * K, (uint32_t)(kPairsPerWarp * K * sizeof(double)));
+        }
+      }
+      if (!pdl) {   // the loads are in flight during the allocation
+        if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)tmem_cols);
+        tmem_meet(true);
+      }
+    }
     __pipeline_wait_prior(0);
     __syncwarp();
     if (!p.times) {
@@ -682,15 +694,12 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
     if (nonfinite) status |= 4;
     status |= __shfl_xor_sync(0xffffffffu, status, 16);
     if (p.status && active && side == 0) p.status[prob] = status;
-    if (base + stride < p.B) {
-      __syncwarp();   // every lane is done with this batch's inputs
-      issue_inputs(base + stride);
-    }
   }
+  if (!tmem_ready) tmem_meet(false);   // a warp without a batch (ragged last CTA)
   if (lane == 0) bulk_wait_read<0>();   // shared memory stays valid until the last copies have read it
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if (warp == 0) tmem_dealloc(tmem_base_slot, (uint32_t)tmem_cols);
 }
 
 #undef H1T
