@@ -157,14 +157,17 @@ inline int tmem_columns(int K) {
   return cols;
 }
 // per-warp shared memory, in doubles, every region a multiple of 128 bytes (the TMA reads the tiles):
-// positions [16][(K+1) D], times [16][K], copy-out tiles [2 buffers][2 sides][16][10 D]
+// two input buffers of positions [16][(K+1) D] + times [16][K] (a warp's next batch arrives during the current
+// one), copy-out tiles [2 buffers][2 sides][16][10 D]
 template <int D>
 struct WarpSmem {
-  size_t pos, tim, tile, total;
+  size_t pos, tim, in_stride, tile, total;
   __host__ __device__ explicit WarpSmem(int K) {
     size_t o = 0;
     pos = o; o += ((size_t)kPairsPerWarp * (K + 1) * D + 15) & ~(size_t)15;
     tim = o; o += ((size_t)kPairsPerWarp * K + 15) & ~(size_t)15;
+    in_stride = o;
+    o += in_stride;   // the second input buffer
     tile = o; o += (size_t)2 * 2 * kPairsPerWarp * D * kN;   // 16 x 80 D bytes is a multiple of 128
     total = o;
   }
@@ -218,15 +221,15 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
 
   const WarpSmem<D> lay(K);
   double* wbase = smem + (size_t)warp * lay.total;
-  double* pos_s = wbase + lay.pos;     // [16][per_pos]
-  double* time_s = wbase + lay.tim;    // [16][K]
+  double* pos_s = wbase + lay.pos;     // [16][per_pos]   (the current batch's buffer; the other one is
+  double* time_s = wbase + lay.tim;    // [16][K]          lay.in_stride further on or back)
   double* tile_s = wbase + lay.tile;   // [2][2][16][kTile]
 
   const long pairs_per_cta = (long)kWarpsPerCta * kPairsPerWarp;
   const long stride = (long)gridDim.x * pairs_per_cta;
   long base = (long)blockIdx.x * pairs_per_cta + (long)warp * kPairsPerWarp;
   // inputs by cp.async: every chunk of a batch in flight before the single wait
-  auto issue_inputs = [&](long b0) {
+  auto issue_inputs = [&](long b0, double* pos_s, double* time_s) {
     const int n = (int)min((long)kPairsPerWarp, p.B - b0);
     if (kExtras && p.chunk_J > 0) {
       // chunks of longer trajectories: every problem's vertices from its own place in the trajectories' array
@@ -286,14 +289,15 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
 
   int buf = 0;
   bool first = true;
+  int in_buf = 0;
   for (; base < p.B; base += stride) {
     const int n_here = (int)min((long)kPairsPerWarp, p.B - base);
     const long prob = base + q;
     const bool active = q < n_here;
-    __syncwarp();   // every lane is done with the previous batch's inputs
-    issue_inputs(base);
+    const long other_in = in_buf ? -(long)lay.in_stride : (long)lay.in_stride;
     if (first) {
       first = false;
+      issue_inputs(base, pos_s, time_s);
       // the batch that will take this warp's place on the SM one wave from now is pulled into L2 (TMA
       // prefetch), so that only the first wave of a launch waits for DRAM
       if (lane == 0 && p.aligned16 && !(kExtras && p.chunk_J > 0)) {
@@ -310,6 +314,11 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
     }
     __pipeline_wait_prior(0);
     __syncwarp();
+    if (base + stride < p.B) {
+      // the warp's next batch arrives in the other buffer while this one is solved (every lane left that
+      // buffer before the __syncwarp above)
+      issue_inputs(base + stride, pos_s + other_in, time_s + other_in);
+    }
     if (!p.times) {
       estimate_times<D>(K, p.v_max, p.a_max, p.magic, p.times_out, pos_s, time_s, base, n_here, lane);
       __syncwarp();
@@ -694,6 +703,10 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
     if (nonfinite) status |= 4;
     status |= __shfl_xor_sync(0xffffffffu, status, 16);
     if (p.status && active && side == 0) p.status[prob] = status;
+    // the next batch is in the other input buffer
+    pos_s += other_in;
+    time_s += other_in;
+    in_buf ^= 1;
   }
   if (!tmem_ready) tmem_meet(false);   // a warp without a batch (ragged last CTA)
   if (lane == 0) bulk_wait_read<0>();   // shared memory stays valid until the last copies have read it
@@ -752,15 +765,24 @@ inline cudaError_t launch_d(FastParams p, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long per_cta = (long)kWarpsPerCta * kPairsPerWarp;
-  long grid = (p.B + per_cta - 1) / per_cta;
-  // one batch of 16 trajectories per warp while the grid stays modest (the hardware CTA scheduler
-  // balances the SMs); very large batches loop
-  const long max_grid = 148L * 64;
-  if (grid > max_grid) grid = max_grid;
+  const long need = (p.B + per_cta - 1) / per_cta;   // CTAs at one batch of 16 trajectories per warp
   int dev = 0, sms = 148, ctas = 2;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, kWarpsPerCta * 32, smem) != cudaSuccess || ctas < 1) ctas = 2;
   if (ctas > 512 / cols) ctas = 512 / cols;   // tensor memory: 512 columns per SM
+  // Above two waves of CTAs a warp takes batches_per_warp batches (the second arrives in the other input
+  // buffer during the first; allocation, table, barrier and the final drain are paid once), and the grid stays a
+  // whole number of waves so that every resident slot ends up with the same number of batches, give or take
+  // one, as under one-batch CTAs: 65,536 solves, grid 1,024 -> 592: 43.2 -> 42.2 us.  (Grids that are not a
+  // multiple of the slots lose to quantisation: 512 CTAs 47.3 us, 342 CTAs 55.8 us.)
+  const long slots = (long)sms * ctas;
+  static const long batches_per_warp = [] { const char* v = std::getenv("MINSNAP_TM_BATCHES"); return v ? std::atol(v) : 2L; }();
+  long grid = need;
+  if (batches_per_warp > 1 && need > 2 * slots) {
+    const long waves = (need + slots - 1) / slots;
+    grid = slots * ((waves + batches_per_warp - 1) / batches_per_warp);
+    if (grid > need) grid = need;
+  }
   // MINSNAP_TM_PDL=0 switches programmatic dependent launch off (A/B measurements)
   static const int pdl = [] { const char* v = std::getenv("MINSNAP_TM_PDL"); return v ? std::atoi(v) : 1; }();
   cudaLaunchConfig_t cfg = {};
