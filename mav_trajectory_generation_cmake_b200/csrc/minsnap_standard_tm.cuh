@@ -29,6 +29,8 @@
 // same summation orders).
 #pragma once
 #include <cuda.h>
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "minsnap_standard_fast.cuh"
@@ -768,8 +770,21 @@ inline cudaError_t launch_d(FastParams p, cudaStream_t stream) {
   const long need = (p.B + per_cta - 1) / per_cta;   // CTAs at one batch of 16 trajectories per warp
   int dev = 0, sms = 148, ctas = 2;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, kWarpsPerCta * 32, smem) != cudaSuccess || ctas < 1) ctas = 2;
-  if (ctas > 512 / cols) ctas = 512 / cols;   // tensor memory: 512 columns per SM
+  {
+    // resident CTAs per SM from the three resources themselves (the occupancy query answers for the current
+    // shared-memory carve-out, not for the one the launch will get)
+    cudaFuncAttributes fa;
+    int regs_per_sm = 65536, smem_per_sm = 228 * 1024;
+    cudaDeviceGetAttribute(&regs_per_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    ctas = 512 / cols;   // tensor memory: 512 columns per SM
+    if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess && fa.numRegs > 0) {
+      const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * kWarpsPerCta * 32;
+      ctas = std::min(ctas, regs_per_sm / regs_per_cta);
+      ctas = std::min(ctas, (int)(smem_per_sm / (smem + fa.sharedSizeBytes + 1024)));
+    }
+    if (ctas < 1) ctas = 1;
+  }
   // Above two waves of CTAs a warp takes batches_per_warp batches (the second arrives in the other input
   // buffer during the first; allocation, table, barrier and the final drain are paid once), and the grid stays a
   // whole number of waves so that every resident slot ends up with the same number of batches, give or take
@@ -785,6 +800,8 @@ inline cudaError_t launch_d(FastParams p, cudaStream_t stream) {
   }
   // MINSNAP_TM_PDL=0 switches programmatic dependent launch off (A/B measurements)
   static const int pdl = [] { const char* v = std::getenv("MINSNAP_TM_PDL"); return v ? std::atoi(v) : 1; }();
+  if (std::getenv("MINSNAP_TM_DEBUG"))
+    std::fprintf(stderr, "tm grid %ld need %ld slots %ld ctas %d sms %d smem %zu cols %d\n", grid, need, slots, ctas, sms, smem, cols);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kWarpsPerCta * 32);
