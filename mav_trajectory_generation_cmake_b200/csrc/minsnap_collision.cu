@@ -123,7 +123,7 @@ __device__ double potential(const CollisionArgs& a, const GridView& g, double x,
 template <int N, bool kGrad>
 __global__ void __launch_bounds__(128) collision_cost_kernel(CollisionArgs a) {
   const int lane = threadIdx.x & 31;
-  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long warp = blockIdx.x * (long)(blockDim.x >> 5) + uniform_warp_index();
   const long n_warps = ((long)gridDim.x * blockDim.x) >> 5;
   GridView g;
   g.data = a.d_sdf; g.nx = a.nx; g.ny = a.ny; g.nz = a.nz;

@@ -24,6 +24,11 @@ namespace minsnap {
 
 constexpr int kWarp = 32;
 
+// threadIdx.x / 32 through a shuffle: the compiler then knows the value is the same in every lane, keeps what is
+// derived from it (batch bases, shared-memory carve-outs, loop bounds) in uniform registers and branches on it
+// without a vote
+__device__ __forceinline__ int uniform_warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 template <int N>
 struct UnitTables;
 

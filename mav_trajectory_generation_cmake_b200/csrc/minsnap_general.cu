@@ -117,7 +117,7 @@ __global__ void segment_matrices_kernel(long n, int delta, const double* __restr
                                         double* __restrict__ Ainv, double* __restrict__ Q, double* __restrict__ H) {
   constexpr int h = N / 2;
   const int lane = threadIdx.x & 31;
-  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long warp = blockIdx.x * (long)(blockDim.x >> 5) + uniform_warp_index();
   const long n_warps = ((long)gridDim.x * blockDim.x) >> 5;
   const double* a1 = UnitTables<N>::a1inv();
   const double* h1 = UnitTables<N>::h1(delta);
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) solve_general_kernel(GeneralKernelParams 
 
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_index();
   const int K = p.K, D = p.D, n_fixed = p.n_fixed, n_free = p.n_free;
   const size_t per_warp = GeneralLayout<N>::per_warp_doubles(K, D, n_fixed, n_free);
 
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(256) cost_kernel(long B, int K, int D, int del
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long warp = blockIdx.x * (long)(blockDim.x >> 5) + uniform_warp_index();
   const long n_warps = ((long)gridDim.x * blockDim.x) >> 5;
   const int total = K * D * N;
   for (long b = warp; b < B; b += n_warps) {

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(SampleKernelPara
   double* stage = seg_start + K;
   double* bc = stage + kSampleWarps * kWarp * per;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_index();
   double* my_stage = stage + warp * kWarp * per;
 
   const long n_work = p.B * p.chunks;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_all_derivatives_kernel(
   double* coef = seg_start + K;
   double* stage = coef + n_c + ((2 * K + n_c) & 1);   // keep the staging area 16-byte aligned
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_index();
   double* my_stage = stage + (size_t)warp * kWarp * per + ((warp * kWarp * per) & 1);
   constexpr double kFactorial[6] = {1.0, 1.0, 2.0, 6.0, 24.0, 120.0};
 
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(128) evaluate_range_kernel(long B, int K, int 
   __shared__ double s_tl[4][kWarp];
   __shared__ double s_acc[4][kWarp];
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
+  const int wib = uniform_warp_index();
   const long warp = blockIdx.x * 4L + wib;
   const long n_warps = gridDim.x * 4L;
   for (long b = warp; b < B; b += n_warps) {

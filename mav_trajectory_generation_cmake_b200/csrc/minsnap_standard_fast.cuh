@@ -271,7 +271,7 @@ template <int D, bool kCoeffs, bool kGlobalSlots = false, bool kCost = true, boo
 __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_index();
   const int warps_per_cta = blockDim.x >> 5;
   const int K = p.K;
   const int pos_stride = (K + 1) * D;

@@ -215,7 +215,7 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   const int lane = threadIdx.x & 31;
   // through a shuffle the compiler knows the warp index is warp-uniform: addresses and batch bases derived from
   // it stay in uniform registers, and the TMA operands need no per-lane vote loop
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int warp = uniform_warp_index();
   const int K = p.K;
   const int per_pos = (K + 1) * D;
   constexpr int kVec = kF * D;    // doubles per vertex vector
@@ -280,6 +280,12 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
     // all of this runs while the predecessor's last CTAs drain
     if (warp == 0) tmem_alloc(&tmem_base_slot, (uint32_t)tmem_cols);
     tmem_meet(false);
+    // L2 is the point of coherence: pulling this warp's first batch towards it before the predecessor has
+    // completed cannot leave a stale copy anywhere, and the first wave's DRAM latency passes during the wait
+    if (lane == 0 && base + kPairsPerWarp <= p.B && p.aligned16 && !(kExtras && p.chunk_J > 0)) {
+      bulk_prefetch_l2(p.positions + base * per_pos, (uint32_t)(kPairsPerWarp * per_pos * sizeof(double)));
+      if (p.times) bulk_prefetch_l2(p.times + base * K, (uint32_t)(kPairsPerWarp * K * sizeof(double)));
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
   }
 
@@ -565,7 +571,8 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
         const double* t0 = tile_s + (size_t)(b * 2) * kPairsPerWarp * kTile;
         tensor_store_3d(&coeff_map, t0, 0, jj, (int)base);
         tensor_store_3d(&coeff_map, t0 + kPairsPerWarp * kTile, 0, K - 1 - jj, (int)base);
-        bulk_commit();
+        // the group is committed where it is next waited for: committed here, the instruction sat ~2 % of
+        // the kernel on the scoreboard of the two stores just issued
       }
     };
     for (int j = mA; j >= 0; --j) {
@@ -661,7 +668,10 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
         if (e9 == 0x7ff00000 || e4 == 0x7ff00000) nonfinite = 1;
       }
       // the copies that read this buffer two steps ago are done with it
-      if (lane == 0) bulk_wait_read<1>();
+      if (lane == 0) {
+        bulk_commit();   // the previous step's two stores
+        bulk_wait_read<1>();
+      }
       __syncwarp();
       {
         double2* t2 = reinterpret_cast<double2*>(tile);
@@ -711,7 +721,10 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
     in_buf ^= 1;
   }
   if (!tmem_ready) tmem_meet(false);   // a warp without a batch (ragged last CTA)
-  if (lane == 0) bulk_wait_read<0>();   // shared memory stays valid until the last copies have read it
+  if (lane == 0) {
+    bulk_commit();
+    bulk_wait_read<0>();   // shared memory stays valid until the last copies have read it
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base_slot, (uint32_t)tmem_cols);
