@@ -258,8 +258,9 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // the recovery table is generated (tools/gen_tables.py) and arrives from global memory by cp.async: nobody
   // waits for it before the first batch's inputs are waited for
-  for (int e = threadIdx.x; e < 2 * kRecTab; e += blockDim.x)
-    __pipeline_memcpy_async(&rec_tab[0][0] + e, minsnap_tables::kRecoveryRoles_N10 + e, 8);
+  static_assert(2 * kRecTab <= kWarpsPerCta * 32, "one table entry per thread");
+  if (threadIdx.x < 2 * kRecTab)
+    __pipeline_memcpy_async(&rec_tab[0][0] + threadIdx.x, minsnap_tables::kRecoveryRoles_N10 + threadIdx.x, 8);
   __pipeline_commit();
   if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&coeff_map)) : "memory");
   // tensor memory: one allocation per CTA (warp 0), every warp works in its own lane quarter.  The warps meet
