@@ -831,7 +831,8 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
         }
       }
       if (kCost && p.cost && mine) {
-        // u^T Hred1 u * T^-7: the per-segment quadratic form in scaled variables
+        // u^T Hred1 u * T^-7: the per-segment quadratic form in scaled variables, over the packed
+        // lower triangle with doubled off-diagonal entries (tools/gen_tables.py): 54 multiply-adds per dimension
         const double i7 = i5 * i2;
         double qsum = 0.0;
 #pragma unroll
@@ -839,13 +840,9 @@ __global__ void __launch_bounds__(128) solve_standard_pair_kernel(FastParams p) 
           double qd = 0.0;
 #pragma unroll
           for (int r = 0; r < 2 * kF + 1; ++r) {
-            const int hr = r == 0 ? 5 : (r <= kF ? r : r + 1);       // row of H1: dp -> 5, start k -> k, end k -> 5 + k
-            double row = 0.0;
+            double row = minsnap_tables::kCostForm_N10_d4[tri(r, r)] * u[r][d];
 #pragma unroll
-            for (int s = 0; s < 2 * kF + 1; ++s) {
-              const int hs = s == 0 ? 5 : (s <= kF ? s : s + 1);
-              row = fma(H1T(hr, hs), u[s][d], row);
-            }
+            for (int s = 0; s < r; ++s) row = fma(minsnap_tables::kCostForm_N10_d4[tri(r, s)], u[s][d], row);
             qd = fma(row, u[r][d], qd);
           }
           qsum += qd;

@@ -681,7 +681,10 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
       }
       double qsum = 0.0;
       if (kCost) {
-        // u^T Hred1 u * T^-7: the per-segment quadratic form in scaled variables
+        // u^T Hred1 u * T^-7: the per-segment quadratic form in scaled variables.  (The packed
+        // lower-triangle form of the first-generation kernel, 54 instead of 90 multiply-adds per dimension, was
+        // measured here too: its 45 extra table constants push uniform-register fills into this loop, 57.4 ->
+        // 62.7 us per 65,536 solves with cost.)
 #pragma unroll
         for (int d = 0; d < D; ++d) {
           double qd = 0.0;

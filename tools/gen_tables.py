@@ -126,6 +126,20 @@ def recovery_roles_n10(Ai):
     return out
 
 
+def cost_form_n10(H):
+    """Packed lower triangle of the per-segment cost form in the kernels' variable order
+    u = [dp, T^k start_k (k = 1..4), T^k end_k (k = 1..4)] (rows of H1: dp -> 5, start k -> k, end k -> 5 + k):
+    entry tri(r, s) = H1[row r][row s] on the diagonal and 2 H1[row r][row s] below it, so that
+    u^T H u = sum_r u_r (sum_{s <= r} table[tri(r, s)] u_s) with 54 multiply-adds instead of 90."""
+    rows = [5, 1, 2, 3, 4, 6, 7, 8, 9]
+    out = []
+    for r in range(9):
+        for s in range(r + 1):
+            v = H[rows[r]][rows[s]]
+            out.append(v if r == s else 2 * v)
+    return out
+
+
 def main():
     with open(OUT, "w") as fh:
         fh.write("// GENERATED by tools/gen_tables.py -- do not edit.\n")
@@ -151,6 +165,12 @@ def main():
                 H = matmul(matmul(AiT, cost_matrix_unit(N, delta)), Ai)
                 assert all(H[i][j] == H[j][i] for i in range(N) for j in range(N))
                 emit_matrix("kH1_N%d_d%d" % (N, delta), H, fh)
+                if N == 10 and delta == 4:
+                    t = cost_form_n10(H)
+                    fh.write("MINSNAP_TABLE_QUAL MINSNAP_TABLE_CONST double kCostForm_N10_d4[45] = {\n")
+                    for r in range(9):
+                        fh.write("    " + ", ".join(lit(x) for x in t[r * (r + 1) // 2:(r + 1) * (r + 2) // 2]) + ",\n")
+                    fh.write("};\n")
             fh.write("\n")
         fh.write("}  // namespace minsnap_tables\n")
     print("wrote", os.path.normpath(OUT))
