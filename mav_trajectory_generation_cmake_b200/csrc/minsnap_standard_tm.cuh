@@ -234,15 +234,23 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   auto issue_inputs = [&](long b0, double* pos_s, double* time_s) {
     const int n = (int)min((long)kPairsPerWarp, p.B - b0);
     if (kExtras && p.chunk_J > 0) {
-      // chunks of longer trajectories: every problem's vertices from its own place in the trajectories' array
-      long t = b0;
-      long traj = t / p.chunk_J;
-      int in_traj = (int)(t - traj * p.chunk_J);
-      for (int r = 0; r < n; ++r) {
-        const double* src = p.positions + (t * K + traj) * D;
-        for (int o = lane; o < per_pos; o += kWarp) __pipeline_memcpy_async(pos_s + r * per_pos + o, src + o, 8);
-        ++t;
-        if (++in_traj == p.chunk_J) { in_traj = 0; ++traj; }
+      // chunks of longer trajectories: every problem's K + 1 vertices from its own place in the trajectories'
+      // array (vertex t K + t / chunk_J on).  The n per_pos elements of the batch are dealt to the lanes 32 at
+      // a time; a lane advances its (problem, offset, chunk-in-trajectory) position incrementally.
+      const long traj0 = b0 / p.chunk_J;
+      const int in0 = (int)(b0 - traj0 * p.chunk_J);
+      int r = lane / per_pos, o = lane - r * per_pos;   // lane < 32: a handful of problems at most
+      int in_traj = in0 + r;
+      long traj = traj0;
+      while (in_traj >= p.chunk_J) { in_traj -= p.chunk_J; ++traj; }
+      while (r < n) {
+        __pipeline_memcpy_async(pos_s + r * per_pos + o, p.positions + ((b0 + r) * K + traj) * D + o, 8);
+        o += kWarp;
+        while (o >= per_pos) {
+          o -= per_pos;
+          ++r;
+          if (++in_traj == p.chunk_J) { in_traj = 0; ++traj; }
+        }
       }
     } else {
       fast::async_copy_doubles(pos_s, p.positions + b0 * per_pos, n * per_pos, lane, p.aligned16);
@@ -321,12 +329,29 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
         tmem_meet(true);
       }
     }
+    // the boundary derivatives of the lane's end of the chain (actual coordinates) are requested before the
+    // inputs are waited for: both latencies pass together
+    const double* bd_src = nullptr;
+    if (kExtras && p.end_derivatives && active) bd_src = p.end_derivatives + (prob * 2 + side) * kVec;
+    double bd_first[kF][D];
+    if (kExtras) {
+#pragma unroll
+      for (int a = 0; a < kF; ++a)
+#pragma unroll
+        for (int d = 0; d < D; ++d) bd_first[a][d] = bd_src ? __ldg(bd_src + a * D + d) : 0.0;
+    }
     __pipeline_wait_prior(0);
     __syncwarp();
     if (base + stride < p.B) {
       // the warp's next batch arrives in the other buffer while this one is solved (every lane left that
       // buffer before the __syncwarp above)
       issue_inputs(base + stride, pos_s + other_in, time_s + other_in);
+      if (kExtras && p.end_derivatives && prob + stride < p.B) {
+        // and its boundary derivatives move towards L1 (the loads at the top of the next batch hit there)
+        const double* nb_src = p.end_derivatives + ((prob + stride) * 2 + side) * kVec;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nb_src));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nb_src + kVec - 1));
+      }
     }
     if (!p.times) {
       estimate_times<D>(K, p.v_max, p.a_max, p.magic, p.times_out, pos_s, time_s, base, n_here, lane);
@@ -341,9 +366,7 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
     auto local_p = [&](int j, int d) { return my_pos[(side ? K - j : j) * D + d]; };
 
     int status = 0;
-    const double* bd_src = nullptr;   // boundary derivatives of the lane's end of the chain (actual coordinates)
-    if (kExtras && p.end_derivatives && active) bd_src = p.end_derivatives + (prob * 2 + side) * kVec;
-    auto bd = [&](int a, int d) { return (kExtras && bd_src) ? flip[a] * bd_src[a * D + d] : 0.0; };
+    auto bd = [&](int a, int d) { return (kExtras && bd_src) ? flip[a] * __ldg(bd_src + a * D + d) : 0.0; };
 
     double xm[kF][D];             // middle block solution, local coordinates; then the far vector of each step
     double Z[kF][kF], w[kF][D];   // after the forward sweep: the lane's LAST block (never leaves the registers)
@@ -387,7 +410,7 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
           for (int d = 0; d < D; ++d) {
             double acc = g[b][d];
 #pragma unroll
-            for (int a = 0; a < kF; ++a) acc = fma(-E0[a][b], bd(a, d), acc);
+            for (int a = 0; a < kF; ++a) acc = fma(-E0[a][b], flip[a] * bd_first[a][d], acc);
             g[b][d] = acc;
           }
       }
