@@ -68,7 +68,7 @@ cudaError_t launch_reorder(int N, int K, long n_masks, const uint8_t* d_mask, in
     cudaError_t e = cudaFuncSetAttribute(reorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const int grid = (int)(n_masks < 148L * 32 ? n_masks : 148L * 32);
+  const int grid = (int)(n_masks < sm_count() * 32 ? n_masks : sm_count() * 32);
   reorder_kernel<<<grid, 32, smem, stream>>>(N, K, n_masks, d_mask, d_col_of_row, d_counts);
   return cudaGetLastError();
 }
@@ -104,7 +104,7 @@ cudaError_t launch_estimate_times(long B, int K, int D, const double* d_position
   if (total == 0) return cudaSuccess;
   const int block = 256;
   long grid = (total + block - 1) / block;
-  if (grid > 148L * 16) grid = 148L * 16;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
   estimate_times_kernel<<<(int)grid, block, 0, stream>>>(total, K, D, d_positions, v_max, a_max, magic, d_times);
   return cudaGetLastError();
 }
@@ -151,7 +151,7 @@ static cudaError_t launch_segment_matrices_n(long n, int delta, const double* d_
                                              double* d_Q, double* d_H, cudaStream_t stream) {
   const int block = 128;
   long grid = (n * 32 + block - 1) / block;
-  if (grid > 148L * 16) grid = 148L * 16;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
   if (grid < 1) grid = 1;
   segment_matrices_kernel<N><<<(int)grid, block, 0, stream>>>(n, delta, d_T, d_A, d_Ainv, d_Q, d_H);
   return cudaGetLastError();
@@ -421,7 +421,7 @@ static cudaError_t launch_general_n(const GeneralSolveArgs& a, cudaStream_t stre
   p.times = a.d_times; p.coeffs = a.d_coeffs; p.free_out = a.d_free_out; p.cost = a.d_cost;
   p.status = a.d_status;
   long grid = (a.B + warps - 1) / warps;
-  const long max_grid = 148L * 32;
+  const long max_grid = sm_count() * 32;
   if (grid > max_grid) grid = max_grid;
   kernel<<<(int)grid, warps * 32, smem, stream>>>(p);
   return cudaGetLastError();
@@ -482,7 +482,7 @@ cudaError_t launch_cost(long B, int K, int D, int N, int derivative, const doubl
   if (B == 0) return cudaSuccess;
   const int block = 256;
   long grid = (B * 32 + block - 1) / block;
-  if (grid > 148L * 16) grid = 148L * 16;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
   MINSNAP_DISPATCH_N(N, (cost_kernel<kN><<<(int)grid, block, 0, stream>>>(B, K, D, derivative, d_coeffs, d_times, d_cost)));
   return cudaGetLastError();
 }

@@ -10,6 +10,19 @@ namespace minsnap {
 // Largest dynamic shared memory a CTA may request on sm_100 (227 KB).
 constexpr size_t kMaxDynamicSmem = 227 * 1024;
 
+// Multiprocessors of the current device (148 on B200), queried once per device: grid caps and the batch-size
+// thresholds between kernels scale with it instead of carrying the number.
+inline long sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cached[dev];
+}
+
 bool supported_n(int N);
 
 // ---- minsnap_general.cu ----------------------------------------------------------------

@@ -248,8 +248,8 @@ static cudaError_t launch_sample_n(const SampleArgs& a, cudaStream_t stream) {
       SampleKernelParams p;
       p.B = a.B; p.K = a.K; p.D = a.D; p.M = a.M; p.n_deriv = a.n_deriv;
       int chunk_len = a.M;
-      if (a.B < 148L * 8) {
-        const long want = (148L * 8 + a.B - 1) / a.B;
+      if (a.B < sm_count() * 8) {
+        const long want = (sm_count() * 8 + a.B - 1) / a.B;
         chunk_len = (int)((a.M + want - 1) / want);
         if (chunk_len < kSampleThreads) chunk_len = kSampleThreads;
         chunk_len = (chunk_len + kWarp - 1) / kWarp * kWarp;
@@ -284,8 +284,8 @@ static cudaError_t launch_sample_n(const SampleArgs& a, cudaStream_t stream) {
   p.B = a.B; p.K = a.K; p.D = a.D; p.M = a.M; p.n_deriv = a.n_deriv;
   // one CTA per trajectory unless that leaves the machine idle: then cut M into chunks
   int chunk_len = a.M;
-  if (a.B < 148L * 8) {
-    const long want = (148L * 8 + a.B - 1) / a.B;
+  if (a.B < sm_count() * 8) {
+    const long want = (sm_count() * 8 + a.B - 1) / a.B;
     chunk_len = (int)((a.M + want - 1) / want);
     const int min_len = kSampleThreads * (use_staged ? 4 : 1);
     if (chunk_len < min_len) chunk_len = min_len;
@@ -405,7 +405,7 @@ cudaError_t launch_evaluate_range(long B, int K, int D, int N, const double* d_c
                                   double* d_out, double* d_t_out, int32_t* d_count, cudaStream_t stream) {
   if (B == 0) return cudaSuccess;
   long grid = (B + 3) / 4;
-  if (grid > 148L * 16) grid = 148L * 16;
+  if (grid > sm_count() * 16) grid = sm_count() * 16;
 #define MINSNAP_ER(N_)                                                                                         \
   case N_:                                                                                                     \
     evaluate_range_kernel<N_><<<(int)grid, 128, 0, stream>>>(B, K, D, d_coeffs, d_times, t_start, t_end, dt,   \

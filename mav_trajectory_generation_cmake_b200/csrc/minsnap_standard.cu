@@ -80,7 +80,7 @@ static cudaError_t generic_route(long B, int S, int K, int D, int N, int derivat
   {
     const long total = B * (long)n_fixed * D;
     long grid = (total + 255) / 256;
-    if (grid > 148L * 16) grid = 148L * 16;
+    if (grid > sm_count() * 16) grid = sm_count() * 16;
     pack_standard_kernel<<<(int)grid, 256, 0, stream>>>(B, K, D, h, d_positions, d_end_derivatives,
                                                         static_cast<double*>(fixed.ptr));
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -167,14 +167,14 @@ cudaError_t launch_solve_standard(const StandardSolveArgs& a, cudaStream_t strea
     const char* which = a.K > fast::kMaxK ? std::getenv("MINSNAP_LONG_CHAIN_KERNEL") : nullptr;
     const int forced = !which ? 0 : std::strcmp(which, "pair") == 0 ? 1 : std::strcmp(which, "bcr") == 0 ? 2
                                   : std::strcmp(which, "chunked") == 0 ? 3 : 0;
-    const bool small_batch = a.B <= 148L * 2 * 19;
+    const bool small_batch = a.B <= sm_count() * 2 * 19;
     // Partitioned route (minsnap_standard_chunked.cuh): chunk Schur complements, separator solve, then every chunk
     // through the headline kernel.  Its four launches cost ~70 us however small the batch; the reduction kernel's
     // ceil(B / 296) x 25 us is below that up to four waves (K = 256: 1,024 -> 0.100 against 0.107 ms, 4,096 ->
     // 0.348 against 0.267 ms, 16,384 -> 1.35 against 0.93 ms).  MINSNAP_LONG_CHAIN_KERNEL=chunked forces it.
     const bool chunk_ok = chunked::supported(a.K, a.D, a.N, a.derivative) && p.aligned16 &&
                           reinterpret_cast<uintptr_t>(a.d_coeffs) % 16 == 0;
-    if (chunk_ok && (forced == 3 || (forced == 0 && a.B > 148L * 2 * 4))) {
+    if (chunk_ok && (forced == 3 || (forced == 0 && a.B > sm_count() * 2 * 4))) {
       double* cost = p.cost;
       p.cost = nullptr;
       if (!p.times) {

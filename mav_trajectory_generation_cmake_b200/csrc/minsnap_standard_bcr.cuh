@@ -556,7 +556,7 @@ inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
   if (e != cudaSuccess) return e;
   // persistent CTAs, as many as are resident at once: each walks its trajectories with the next
   // one's inputs in flight (a CTA per trajectory would leave the cp.async prefetch nothing to fetch)
-  const long resident = 148L * (kMaxDynamicSmem + 1024 >= 2 * (smem + 1024) ? 2 : 1);
+  const long resident = sm_count() * (kMaxDynamicSmem + 1024 >= 2 * (smem + 1024) ? 2 : 1);
   long grid = p.B < resident ? p.B : resident;
   solve_standard_bcr_kernel<D><<<(int)grid, threads, smem, stream>>>(p);
   return cudaGetLastError();

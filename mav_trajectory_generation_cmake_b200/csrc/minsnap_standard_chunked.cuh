@@ -689,7 +689,7 @@ inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
   if (p.free_out) {
     const long total = n_ch * (m - 1) * kVec;
     long grid = (total + 255) / 256;
-    if (grid > 148L * 32) grid = 148L * 32;
+    if (grid > sm_count() * 32) grid = sm_count() * 32;
     scatter_chunk_free_kernel<<<(unsigned)grid, 256, 0, stream>>>(p.B, K, m, kVec, chunk_free, p.free_out);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }

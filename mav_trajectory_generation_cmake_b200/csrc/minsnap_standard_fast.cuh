@@ -921,7 +921,7 @@ inline cudaError_t launch_mode(FastParams p, cudaStream_t stream) {
   // One batch of 16 trajectories per warp while the grid stays modest: the hardware CTA scheduler
   // then balances the SMs dynamically (measured: a fixed persistent grid loses ~8% to the
   // 4.6-batches-per-slot tail at 65,536 problems).  Very large batches loop with prefetch.
-  const long max_grid = 148L * 256;
+  const long max_grid = sm_count() * 256;
   if (grid > max_grid) grid = max_grid;
   void* scratch = nullptr;
   if (kGlobalSlots) {
