@@ -695,6 +695,69 @@ def test_two_kernel_generations_agree(ms, oracle, torch_cuda, monkeypatch, K, D)
         assert coeff_rel_err(a["coeffs"][i].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
 
 
+@pytest.mark.parametrize("K,D", [(4, 2), (12, 1), (10, 3)])
+def test_two_batches_per_warp(ms, oracle, torch_cuda, monkeypatch, K, D):
+    """Above two waves of CTAs a warp of the second-generation kernel takes two batches (second input buffer,
+    one allocation / table / drain per CTA): a ragged batch just above that threshold against the first-generation
+    kernel, with non-zero end derivatives, cost, free derivatives and device-side times."""
+    torch = torch_cuda
+    B = 2 * 296 * 64 + 5 * 64 + 7
+    rng = np.random.default_rng(999 + 10 * K + D)
+    steps = rng.uniform(1.0, 4.0, size=(B, K + 1, D)) * rng.choice([-1.0, 1.0], size=(B, K + 1, D))
+    pos = np.cumsum(steps, axis=1)
+    end = rng.uniform(-1.0, 1.0, size=(B, 2, 4, D))
+    pos_d, end_d = dev(torch, pos), dev(torch, end)
+    results = {}
+    for name in ("tm", "pair"):
+        if name == "pair":
+            monkeypatch.setenv("MINSNAP_STANDARD_KERNEL", "pair")
+        results[name] = ms.solve_standard(pos_d, None, end_derivatives=end_d, v_max=3.0, a_max=5.0, want_cost=True,
+                                          want_free=True, want_times=True)
+        torch.cuda.synchronize()
+    monkeypatch.delenv("MINSNAP_STANDARD_KERNEL")
+    a, b = results["tm"], results["pair"]
+    assert int((a["status"] != 0).sum()) == 0 and int((b["status"] != 0).sum()) == 0
+    assert torch.equal(a["times"], b["times"])
+    ca, cb = a["coeffs"], b["coeffs"]
+    scale = cb.abs().amax(dim=3, keepdim=True).clamp_min(1e-300)
+    assert float(((ca - cb).abs() / scale).max()) <= 1e-10
+    assert float((a["cost"] / b["cost"] - 1.0).abs().max()) <= 1e-10
+    assert float((a["free_values"] - b["free_values"]).abs().max()) <= 1e-12 * max(1.0, float(b["free_values"].abs().max()))
+    # the last, ragged batch against the oracle
+    t = a["times"].cpu().numpy()
+    mask = standard_mask(K)
+    for i in (0, B - 1):
+        vals = np.zeros((K + 1, 5, D))
+        vals[:, 0, :] = pos[i]
+        vals[0, 1:, :] = end[i, 0]
+        vals[K, 1:, :] = end[i, 1]
+        ref = oracle.solve(10, K, D, 4, mask, vals, t[i])
+        assert coeff_rel_err(a["coeffs"][i].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
+
+
+def test_partitioned_route_two_batches_per_warp(ms, torch_cuda, monkeypatch):
+    """The partitioned long-chain route with more chunks than two waves of the headline kernel (4,800 x K = 64 is
+    38,400 chunks of 8 segments, 8 per trajectory: a warp's batch of 16 chunks spans two trajectories) against the
+    cyclic-reduction kernel."""
+    torch = torch_cuda
+    B, K, D = 4800, 64, 3
+    rng = np.random.default_rng(31337)
+    pos = np.cumsum(rng.uniform(0.3, 2.0, (B, K + 1, D)) * rng.choice([-1.0, 1.0], (B, K + 1, D)), axis=1)
+    ends = rng.normal(size=(B, 2, 4, D))
+    outs = {}
+    for which in ("bcr", "chunked"):
+        monkeypatch.setenv("MINSNAP_LONG_CHAIN_KERNEL", which)
+        outs[which] = ms.solve_standard(dev(torch, pos), None, end_derivatives=dev(torch, ends), v_max=3.0, a_max=5.0,
+                                        want_cost=True)
+        torch.cuda.synchronize()
+    monkeypatch.delenv("MINSNAP_LONG_CHAIN_KERNEL")
+    a, b = outs["bcr"], outs["chunked"]
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    scale = a["coeffs"].abs().amax(dim=3, keepdim=True).clamp_min(1e-300)
+    assert float(((a["coeffs"] - b["coeffs"]).abs() / scale).max()) <= 1e-9
+    assert float((a["cost"] / b["cost"] - 1.0).abs().max()) <= 1e-9
+
+
 def test_second_generation_status_bits(ms, torch_cuda):
     """A non-positive segment time is flagged by the recovery phase of the second-generation kernel."""
     torch = torch_cuda
