@@ -627,78 +627,164 @@ struct Scratch {
   }
 };
 
-// p.times must be set (the caller estimates them first when they are computed on the device); p.cost is handled by
-// the caller from the coefficients.  cudaErrorNotSupported: the headline kernel could not take the chunks.
+// Two internal streams per host thread and device (created once, never destroyed before the thread ends): the
+// sub-batches of a call run their kernel chains side by side, so that the latency-bound separator solve of one --
+// a 31-block chain on one warp per 16 trajectories -- overlaps the throughput-bound kernels of the other.  The fork
+// and the join are events on the caller's stream: stream order as the caller sees it is unchanged, and the whole
+// thing is capturable into a CUDA graph.
+struct SideStreams {
+  static constexpr int kN = 4;
+  int device = -1;
+  cudaStream_t s[kN] = {};
+  cudaEvent_t fork = nullptr, join[kN] = {};
+  bool ready() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (device == dev) return true;
+    if (device >= 0) return false;   // one device per thread; another device takes the single-stream path
+    for (int i = 0; i < kN; ++i) {
+      if (cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) != cudaSuccess) return false;
+    }
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
+    device = dev;
+    return true;
+  }
+};
+inline SideStreams& side_streams() {
+  static thread_local SideStreams st;
+  return st;
+}
+
+// One contiguous range of trajectories through the three steps on stream `s`; every scratch array was allocated by
+// the caller (on the caller's stream, before the fork).
 template <int D>
-inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
+struct RangeScratch {
+  double *rec, *ends, *slots, *sep_blocks, *sep_edge, *sep_middle, *chunk_free;
+  int32_t *st_chunk, *st_extra;
+};
+
+template <int D>
+inline cudaError_t run_range(const FastParams& p, const RangeScratch<D>& w, cudaStream_t s) {
   const int K = p.K, m = chunk_segments(K), J = K / m;
   const long n_ch = p.B * J;
   constexpr int kVec = kF * D;
+  using L = SepLayout<D>;
   cudaError_t e;
-  Scratch rec, ends, st_chunk, st_extra, slots, sep_blocks, sep_edge, sep_middle;
-  if ((e = rec.alloc(sizeof(double) * (size_t)Fields<D>::kCount * n_ch, stream)) != cudaSuccess) return e;
-  if ((e = ends.alloc(sizeof(double) * (size_t)n_ch * 2 * kVec, stream)) != cudaSuccess) return e;
-  if ((e = st_chunk.alloc(sizeof(int32_t) * (size_t)n_ch, stream)) != cudaSuccess) return e;
-  if ((e = st_extra.alloc(sizeof(int32_t) * (size_t)p.B, stream)) != cudaSuccess) return e;
-  int32_t* extra = static_cast<int32_t*>(st_extra.ptr);
-  if ((e = cudaMemsetAsync(extra, 0, sizeof(int32_t) * (size_t)p.B, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(w.st_extra, 0, sizeof(int32_t) * (size_t)p.B, s)) != cudaSuccess) return e;
   {
     const dim3 grid((unsigned)((n_ch + 127) / 128), 2);
-    chunk_schur_kernel<D><<<grid, 128, 0, stream>>>(p.B, K, m, p.positions, p.times, static_cast<double*>(rec.ptr), extra);
+    chunk_schur_kernel<D><<<grid, 128, 0, s>>>(p.B, K, m, p.positions, p.times, w.rec, w.st_extra);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   {
-    using L = SepLayout<D>;
-    const int ns = J - 1, mA = ns / 2;
-    if ((e = sep_blocks.alloc(sizeof(double) * (size_t)mA * L::kBlock * 2 * p.B, stream)) != cudaSuccess) return e;
-    if ((e = sep_edge.alloc(sizeof(double) * (size_t)16 * 2 * p.B, stream)) != cudaSuccess) return e;
-    if ((e = sep_middle.alloc(sizeof(double) * (size_t)L::kMid * p.B, stream)) != cudaSuccess) return e;
-    assemble_separators_kernel<D><<<(unsigned)((p.B * ns + 127) / 128), 128, 0, stream>>>(
-        p.B, K, m, p.positions, p.times, static_cast<const double*>(rec.ptr), static_cast<double*>(sep_blocks.ptr),
-        static_cast<double*>(sep_edge.ptr), static_cast<double*>(sep_middle.ptr));
+    const int ns = J - 1;
+    assemble_separators_kernel<D><<<(unsigned)((p.B * ns + 127) / 128), 128, 0, s>>>(p.B, K, m, p.positions, p.times, w.rec,
+                                                                                     w.sep_blocks, w.sep_edge, w.sep_middle);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    const unsigned grid = (unsigned)((p.B + 15) / 16);
-    const int stored = mA > 1 ? mA - 1 : 0;
-    if ((e = slots.alloc(sizeof(double) * (size_t)grid * stored * (kF * kF + kVec) * 32, stream)) != cudaSuccess) return e;
-    separator_solve_kernel<D><<<grid, 32, 0, stream>>>(
-        p.B, K, m, p.end_derivatives, static_cast<const double*>(sep_blocks.ptr), static_cast<const double*>(sep_edge.ptr),
-        static_cast<const double*>(sep_middle.ptr), static_cast<double*>(ends.ptr), p.free_out,
-        static_cast<double*>(slots.ptr), extra);
+    separator_solve_kernel<D><<<(unsigned)((p.B + 15) / 16), 32, 0, s>>>(p.B, K, m, p.end_derivatives, w.sep_blocks, w.sep_edge,
+                                                                         w.sep_middle, w.ends, p.free_out, w.slots, w.st_extra);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   FastParams q = p;
   q.B = n_ch;
   q.K = m;
   q.chunk_J = J;   // the headline kernel picks every chunk's vertices out of the trajectories' own array
-  q.end_derivatives = static_cast<const double*>(ends.ptr);
+  q.end_derivatives = w.ends;
   q.times_out = nullptr;
   q.cost = nullptr;
-  q.status = p.status ? static_cast<int32_t*>(st_chunk.ptr) : nullptr;
+  q.status = p.status ? w.st_chunk : nullptr;
   q.sweep_S = 0;
   q.aligned16 = (reinterpret_cast<uintptr_t>(p.times) % 16 == 0) && (reinterpret_cast<uintptr_t>(p.coeffs) % 16 == 0);
   // the chunks' interior free derivatives land in [B J][m-1][4][D]; the trajectory's array interleaves the
   // separators, so a caller asking for them gets them through the scatter below
-  double* chunk_free = nullptr;
-  Scratch free_scratch;
-  if (p.free_out) {
-    if ((e = free_scratch.alloc(sizeof(double) * (size_t)n_ch * (m - 1) * kVec, stream)) != cudaSuccess) return e;
-    chunk_free = static_cast<double*>(free_scratch.ptr);
-  }
-  q.free_out = chunk_free;
-  if ((e = tm::launch(q, D, stream)) != cudaSuccess) return e;
+  q.free_out = p.free_out ? w.chunk_free : nullptr;
+  if ((e = tm::launch(q, D, s)) != cudaSuccess) return e;
   if (p.free_out) {
     const long total = n_ch * (m - 1) * kVec;
     long grid = (total + 255) / 256;
     if (grid > sm_count() * 32) grid = sm_count() * 32;
-    scatter_chunk_free_kernel<<<(unsigned)grid, 256, 0, stream>>>(p.B, K, m, kVec, chunk_free, p.free_out);
+    scatter_chunk_free_kernel<<<(unsigned)grid, 256, 0, s>>>(p.B, K, m, kVec, w.chunk_free, p.free_out);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if (p.status) {
-    fold_chunk_status_kernel<<<(unsigned)((p.B + 127) / 128), 128, 0, stream>>>(p.B, J, static_cast<const int32_t*>(st_chunk.ptr),
-                                                                                extra, p.status);
+    fold_chunk_status_kernel<<<(unsigned)((p.B + 127) / 128), 128, 0, s>>>(p.B, J, w.st_chunk, w.st_extra, p.status);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
+  (void)sizeof(L);
   return cudaSuccess;
+}
+
+// p.times must be set (the caller estimates them first when they are computed on the device); p.cost is handled by
+// the caller from the coefficients.  cudaErrorNotSupported: the headline kernel could not take the chunks.
+template <int D>
+inline cudaError_t launch_d(const FastParams& p, cudaStream_t stream) {
+  const int K = p.K, m = chunk_segments(K), J = K / m;
+  constexpr int kVec = kF * D;
+  using L = SepLayout<D>;
+  const int ns = J - 1, mA = ns / 2;
+  const int stored = mA > 1 ? mA - 1 : 0;
+  // Sub-batches: two from 2,048 trajectories on (each still fills the machine in its Schur and chunk kernels); the
+  // ranges are multiples of 16 trajectories so that every array of a range keeps its alignment.  Measured at
+  // K = 256: 4,096 trajectories 247 -> 232 us, 16,384 848 -> 805 us; three and four sub-batches 237 / 812 us.
+  // MINSNAP_CHUNKED_LANES=1 switches the side streams off, 3 or 4 ask for more (A/B measurements).
+  static const int want_lanes = [] { const char* v = std::getenv("MINSNAP_CHUNKED_LANES"); return v ? std::atoi(v) : 2; }();
+  int lanes = 1;
+  if (want_lanes > 1 && p.B >= 2048 && side_streams().ready()) lanes = want_lanes < SideStreams::kN ? want_lanes : SideStreams::kN;
+  while (lanes > 1 && p.B / lanes < 1024) --lanes;
+  long first[SideStreams::kN + 1];
+  for (int i = 0; i <= lanes; ++i) first[i] = i == lanes ? p.B : ((p.B * i / lanes) + 15) / 16 * 16;
+
+  cudaError_t e;
+  Scratch rec, ends, st_chunk, st_extra, slots, sep_blocks, sep_edge, sep_middle, free_scratch;
+  const long n_ch = p.B * J;
+  const long warps16 = (p.B + 15) / 16 + lanes;   // every range rounds its warp count up
+  if ((e = rec.alloc(sizeof(double) * (size_t)Fields<D>::kCount * n_ch, stream)) != cudaSuccess) return e;
+  if ((e = ends.alloc(sizeof(double) * (size_t)n_ch * 2 * kVec, stream)) != cudaSuccess) return e;
+  if ((e = st_chunk.alloc(sizeof(int32_t) * (size_t)n_ch, stream)) != cudaSuccess) return e;
+  if ((e = st_extra.alloc(sizeof(int32_t) * (size_t)p.B, stream)) != cudaSuccess) return e;
+  if ((e = sep_blocks.alloc(sizeof(double) * (size_t)mA * L::kBlock * 2 * p.B, stream)) != cudaSuccess) return e;
+  if ((e = sep_edge.alloc(sizeof(double) * (size_t)16 * 2 * p.B, stream)) != cudaSuccess) return e;
+  if ((e = sep_middle.alloc(sizeof(double) * (size_t)L::kMid * p.B, stream)) != cudaSuccess) return e;
+  if ((e = slots.alloc(sizeof(double) * (size_t)warps16 * stored * (kF * kF + kVec) * 32, stream)) != cudaSuccess) return e;
+  if (p.free_out && (e = free_scratch.alloc(sizeof(double) * (size_t)n_ch * (m - 1) * kVec, stream)) != cudaSuccess) return e;
+
+  SideStreams& ss = side_streams();
+  if (lanes > 1 && (e = cudaEventRecord(ss.fork, stream)) != cudaSuccess) return e;
+  cudaError_t result = cudaSuccess;
+  for (int i = 0; i < lanes; ++i) {
+    const long b0 = first[i], nb = first[i + 1] - first[i];
+    if (nb <= 0) continue;
+    FastParams r = p;
+    r.B = nb;
+    r.positions = p.positions + b0 * (long)(K + 1) * D;
+    r.times = p.times + b0 * K;
+    r.coeffs = p.coeffs + b0 * (long)K * D * fast::kN;
+    r.end_derivatives = p.end_derivatives ? p.end_derivatives + b0 * 2 * kVec : nullptr;
+    r.free_out = p.free_out ? p.free_out + b0 * (long)(K - 1) * kVec : nullptr;
+    r.status = p.status ? p.status + b0 : nullptr;
+    // the record arrays are [field][chunk][trajectory of the range]: every range owns a contiguous slice of each
+    RangeScratch<D> w;
+    w.rec = static_cast<double*>(rec.ptr) + (size_t)Fields<D>::kCount * J * b0;
+    w.ends = static_cast<double*>(ends.ptr) + (size_t)b0 * J * 2 * kVec;
+    w.st_chunk = static_cast<int32_t*>(st_chunk.ptr) + (size_t)b0 * J;
+    w.st_extra = static_cast<int32_t*>(st_extra.ptr) + b0;
+    w.sep_blocks = static_cast<double*>(sep_blocks.ptr) + (size_t)mA * L::kBlock * 2 * b0;
+    w.sep_edge = static_cast<double*>(sep_edge.ptr) + (size_t)16 * 2 * b0;
+    w.sep_middle = static_cast<double*>(sep_middle.ptr) + (size_t)L::kMid * b0;
+    w.slots = static_cast<double*>(slots.ptr) + (size_t)(b0 / 16 + i) * stored * (kF * kF + kVec) * 32;
+    w.chunk_free = p.free_out ? static_cast<double*>(free_scratch.ptr) + (size_t)b0 * J * (m - 1) * kVec : nullptr;
+    cudaStream_t s = lanes > 1 ? ss.s[i] : stream;
+    if (lanes > 1 && (e = cudaStreamWaitEvent(s, ss.fork, 0)) != cudaSuccess) { result = e; break; }
+    e = run_range<D>(r, w, s);
+    if (lanes > 1) {
+      // join whatever was enqueued, also after an error: the caller's stream must not run ahead of the side streams
+      cudaEventRecord(ss.join[i], s);
+      cudaStreamWaitEvent(stream, ss.join[i], 0);
+    }
+    if (e != cudaSuccess) { result = e; break; }
+  }
+  return result;
 }
 
 inline cudaError_t launch(const FastParams& p, int D, cudaStream_t stream) {
