@@ -102,3 +102,47 @@ def test_product_package_does_not_import_oracle():
                     if re.search(r"oracle_py|liboracle|orc_\w+\(|from oracle|import oracle", text):
                         offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
+
+
+def test_generated_tables_are_in_sync_and_consistent(tmp_path, oracle):
+    """csrc/minsnap_tables.h is what tools/gen_tables.py writes (exact rational arithmetic), and the two derived
+    tables the kernels read -- the per-lane-role recovery constants and the packed cost form -- agree with A1inv and
+    H1 as the oracle forms them (ref LIN.i:101-111, 132-169, 573-589)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_tables", os.path.join(root, "tools", "gen_tables.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    tracked = open(gen.OUT).read()
+    gen.OUT = str(tmp_path / "minsnap_tables.h")
+    gen.main()
+    assert open(gen.OUT).read() == tracked, "run python tools/gen_tables.py"
+
+    def table(name):
+        m = re.search(name + r"\[\d+\] = \{(.*?)\};", tracked, re.S)
+        return np.array([float(x) for x in m.group(1).replace("\n", " ").split(",") if x.strip()])
+
+    a1 = table("kA1inv_N10").reshape(10, 10)
+    h1 = table("kH1_N10_d4").reshape(10, 10)
+    A = np.array(oracle.mapping_matrix(10, 1.0)).reshape(10, 10)
+    assert np.abs(a1 @ A - np.eye(10)).max() <= 1e-9
+    H = np.array(oracle.segment_hessian(10, 4, 1.0)).reshape(10, 10)
+    assert np.abs(h1 - H).max() <= 1e-7 * np.abs(H).max()   # the oracle's A^-T Q A^-1 carries the cancellation
+    roles = table("kRecoveryRoles_N10").reshape(2, 54)
+    sign = np.array([-1.0, 1.0, -1.0, 1.0])
+    for i in range(5, 10):
+        for role in (0, 1):
+            row = roles[role, (i - 5) * 9:(i - 4) * 9]
+            assert row[0] == a1[i, 5]
+            new_cols, old_cols = (a1[i, 6:10], a1[i, 1:5]) if role else (a1[i, 1:5], a1[i, 6:10])
+            flip = sign if role else np.ones(4)
+            assert np.array_equal(row[1:5], flip * new_cols) and np.array_equal(row[5:9], flip * old_cols)
+    diag = np.array([a1[k, k] for k in range(1, 5)])
+    assert np.array_equal(roles[0, 45:49], diag) and np.array_equal(roles[1, 49:53], sign * diag)
+    assert not roles[0, 49:53].any() and not roles[1, 45:49].any()
+    cost = table("kCostForm_N10_d4")
+    rows = [5, 1, 2, 3, 4, 6, 7, 8, 9]
+    u = np.random.default_rng(3).normal(size=9)
+    packed = sum(u[r] * sum(cost[r * (r + 1) // 2 + s] * u[s] for s in range(r + 1)) for r in range(9))
+    full = sum(h1[rows[r], rows[s]] * u[r] * u[s] for r in range(9) for s in range(9))
+    assert abs(packed / full - 1.0) <= 1e-12
