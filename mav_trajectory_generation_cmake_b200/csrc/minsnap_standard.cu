@@ -101,7 +101,7 @@ bool standard_supported(int K, int D, int N, int derivative) {
 }
 
 // Kernel choice for the fast route with coefficients: the second-generation kernel (block storage in
-// tensor memory, coefficients out through the TMA; minsnap_standard_tm.cuh) where it applies -- even K
+// tensor memory, coefficients out through the TMA; minsnap_standard_tm.cuh) where it applies -- K = 2 or 4 <= K
 // up to 12 and a 16-byte aligned coefficient array -- else the first-generation two-lane kernel.
 // MINSNAP_STANDARD_KERNEL=pair forces the first generation (A/B measurements).
 static bool use_tm_kernel(const fast::FastParams& p, int D, int N, int derivative) {

@@ -1,4 +1,4 @@
-// Standard-mask solve, second generation (N = 10, snap, even K <= 12): the thread-pair
+// Standard-mask solve, second generation (N = 10, snap, K = 2 or 4 <= K <= 12): the thread-pair
 // elimination of minsnap_standard_fast.cuh with the cost ncu attributed to its output removed --
 // per-lane coefficient stores, every lane of a store instruction in its own 128-byte line.
 //
@@ -21,9 +21,11 @@
 //    known), so x never leaves the registers and the 15 independent dot-product chains of a
 //    dimension fill the FP64 pipe while the next block's TMEM loads are in flight.
 //
-// Control flow is uniform across the warp (even K: both lanes of a pair eliminate the same number
-// of blocks), which the warp-collective tcgen05.ld/st require.  Other shapes (odd K, K = 1,
-// K > 12, the cost sweep, unaligned outputs) keep the first-generation kernel.
+// The tcgen05.ld/st are warp-collective with one address, so both lanes of a pair use tensor-memory slot j - 1 in
+// iteration j.  Even K: both eliminate the same number of blocks.  Odd K (template parameter): the bottom-up lane
+// has one block less, sits out the first forward iteration and the last recovery step, and its half of that
+// step's tile is not sent.  Other shapes (K = 1, K = 3, K > 12, the cost sweep, unaligned outputs) keep the
+// first-generation kernel.
 //
 // Arithmetic is that of minsnap_standard_fast.cuh (same closed-form blocks, same 2x2-Schur inverse,
 // same summation orders).
@@ -197,7 +199,7 @@ __device__ __noinline__ void estimate_times(int K, double v_max, double a_max, d
   }
 }
 
-template <int D, bool kCost, bool kExtras>
+template <int D, bool kCost, bool kExtras, bool kOdd = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const __grid_constant__ CUtensorMap coeff_map,
                          int pdl) {
@@ -300,8 +302,14 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
 
   const int side = lane >> 4;   // 0: top-down lane, 1: bottom-up lane
   const int q = lane & 15;      // trajectory of the batch
-  const int nb = K - 1;         // unknown blocks (odd)
-  const int mA = nb / 2;        // blocks eliminated by either lane; the middle block is vertex mA + 1
+  const int nb = K - 1;         // unknown blocks
+  const int mA = nb / 2;        // blocks eliminated by the top-down lane; the middle block is vertex mA + 1
+  // Odd K: the bottom-up lane has one block (and one segment) less.  It sits out the FIRST forward iteration and the
+  // LAST recovery step (local index jj = j - late), so that both lanes store / load tensor memory slot j - 1 in
+  // iteration j -- the tcgen05 operations are warp-collective with one address -- and both reach their last block
+  // (the one that stays in registers) in the same iteration.
+  constexpr int odd = kOdd ? 1 : 0;       // a template parameter: the even-K instantiations carry none of this
+  const int late = kOdd ? side : 0;       // per lane
   const double flip[kF] = {side ? -1.0 : 1.0, 1.0, side ? -1.0 : 1.0, 1.0};   // (-1)^k, k = 1..4, bottom-up lane
 
   int buf = 0;
@@ -415,16 +423,19 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
           }
       }
       for (int j = 1; j <= mA; ++j) {
-        // here: tp_prev = segment j-1, tp_next = segment j, S/g = reduced block j
-        const bool more = j < mA;
+        // here (jj = j - late >= 1): tp_prev = segment jj-1, tp_next = segment jj, S/g = reduced block jj
+        const bool more = j < mA;        // warp-uniform: the lane's own last block is jj = mA - late
+        const int jj = j - late;
+        const bool mine = jj >= 1;
         TimePowers tp_new;
         double dp_new[D];
-        tp_new.set(local_T(more ? j + 1 : j));
+        double E[kF][kF];
+        if (mine) {
+        tp_new.set(local_T(more ? jj + 1 : jj));
 #pragma unroll
-        for (int d = 0; d < D; ++d) dp_new[d] = more ? local_p(j + 2, d) - local_p(j + 1, d) : 0.0;
+        for (int d = 0; d < D; ++d) dp_new[d] = more ? local_p(jj + 2, d) - local_p(jj + 1, d) : 0.0;
         double Si[10];
         if (!fast::spd4_inverse(S, Si)) status |= 1;
-        double E[kF][kF];
         fast::coupling_block(tp_next, E);
 #pragma unroll
         for (int b = 0; b < kF; ++b) {
@@ -442,10 +453,12 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
 #pragma unroll
           for (int a = 0; a < kF; ++a) w[a][d] = col[a];
         }
-        if (more) {
-          // block j goes to tensor memory: Z at column (j-1) pitch, w right behind it
-          tmem_store_block<D>(taddr + (uint32_t)((j - 1) * block_columns<D>()), Z, w);
-          // advance to block j+1: D_{j+1} - E^T Z,  b_{j+1} - E^T w
+        }
+        // block jj goes to tensor memory slot j - 1: Z at column (j-1) pitch, w right behind it (every lane takes
+        // part; a lane that sat this iteration out parks zeros it never reads)
+        if (more) tmem_store_block<D>(taddr + (uint32_t)((j - 1) * block_columns<D>()), Z, w);
+        if (more && mine) {
+          // advance to block jj+1: D_{jj+1} - E^T Z,  b_{jj+1} - E^T w
           tp_prev = tp_next;
           tp_next = tp_new;
 #pragma unroll
@@ -594,15 +607,18 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
       if (lane == 0) {
         const double* t0 = tile_s + (size_t)(b * 2) * kPairsPerWarp * kTile;
         tensor_store_3d(&coeff_map, t0, 0, jj, (int)base);
-        tensor_store_3d(&coeff_map, t0 + kPairsPerWarp * kTile, 0, K - 1 - jj, (int)base);
+        // the bottom-up rows hold local segment jj - odd (odd K: none in the last step)
+        if (jj - odd >= 0) tensor_store_3d(&coeff_map, t0 + kPairsPerWarp * kTile, 0, K - 1 - (jj - odd), (int)base);
         // the group is committed where it is next waited for: committed here, the instruction sat ~2 % of
         // the kernel on the scoreboard of the two stores just issued
       }
     };
     for (int j = mA; j >= 0; --j) {
+      const int jj = j - late;          // the lane's local vertex / segment of this step; -1: the lane sits it out
+      const int jc = jj > 0 ? jj : 0;   // (it then repeats its step 0 into a tile row that is never sent)
       double x_near[kF][D];
-      if (j >= 1) {
-        if (j < mA) tmem_load_block<D>(taddr + (uint32_t)((j - 1) * block_columns<D>()), Z, w);
+      if (j >= 1 && j < mA) tmem_load_block<D>(taddr + (uint32_t)((j - 1) * block_columns<D>()), Z, w);
+      if (jj >= 1) {
 #pragma unroll
         for (int a = 0; a < kF; ++a)
 #pragma unroll
@@ -613,7 +629,7 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
             x_near[a][d] = acc;
           }
         if (kExtras && p.free_out && active) {
-          const int v = side ? K - j : j;   // actual vertex
+          const int v = side ? K - jj : jj;   // actual vertex
           double* dst = p.free_out + (prob * (long)nb + (v - 1)) * kVec;
 #pragma unroll
           for (int a = 0; a < kF; ++a)
@@ -636,7 +652,7 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
       }
       // recovery of local segment j (ref updateSegmentsFromCompactConstraints, LIN.i:252-273) in ACTUAL
       // orientation: the bottom-up lane's segment starts at its far vertex; odd derivatives change sign.
-      const int seg = side ? K - 1 - j : j;
+      const int seg = side ? K - 1 - jc : jc;
       const double T = my_time[seg];
       if (!(T > 0.0)) status |= 2;   // MINSNAP_STATUS_BAD_TIME; the two lanes cover all K segments
       const double T2 = T * T, T3 = T2 * T, T4 = T2 * T2;
@@ -725,7 +741,7 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
           qsum += qd;
         }
       }
-      if (kCost) cost_acc = fma(qsum, i5 * i2, cost_acc);
+      if (kCost && jj >= 0) cost_acc = fma(qsum, i5 * i2, cost_acc);
       pending_j = j;   // this step's tile leaves during the next step (or after the loop)
       buf ^= 1;
 #pragma unroll
@@ -761,7 +777,8 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
 #undef A1T
 
 inline bool supported(int K, int D, int N, int derivative) {
-  return N == 10 && derivative == 4 && D >= 1 && D <= 3 && K >= 2 && K <= kMaxK && (K % 2) == 0;
+  // even K from 2, odd K from 5 (K = 3 leaves the bottom-up lane without a block: first-generation kernel)
+  return N == 10 && derivative == 4 && D >= 1 && D <= 3 && K >= 2 && K <= kMaxK && K != 3;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -801,9 +818,13 @@ inline cudaError_t launch_d(FastParams p, cudaStream_t stream) {
   if (!make_coeff_map(&map, p.coeffs, p.B, p.K, D)) return cudaErrorNotSupported;
   const int cols = tmem_columns<D>(p.K);
   const bool extras = p.end_derivatives || p.free_out;
-  void (*kernel)(FastParams, int, int, const CUtensorMap, int) =
-      extras ? (p.cost ? solve_standard_tm_kernel<D, true, true> : solve_standard_tm_kernel<D, false, true>)
-             : (p.cost ? solve_standard_tm_kernel<D, true, false> : solve_standard_tm_kernel<D, false, false>);
+  void (*kernel)(FastParams, int, int, const CUtensorMap, int);
+  if (p.K & 1)
+    kernel = extras ? (p.cost ? solve_standard_tm_kernel<D, true, true, true> : solve_standard_tm_kernel<D, false, true, true>)
+                    : (p.cost ? solve_standard_tm_kernel<D, true, false, true> : solve_standard_tm_kernel<D, false, false, true>);
+  else
+    kernel = extras ? (p.cost ? solve_standard_tm_kernel<D, true, true> : solve_standard_tm_kernel<D, false, true>)
+                    : (p.cost ? solve_standard_tm_kernel<D, true, false> : solve_standard_tm_kernel<D, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long per_cta = (long)kWarpsPerCta * kPairsPerWarp;

@@ -653,10 +653,11 @@ def test_solve_standard_other_dimensions(ms, oracle, torch_cuda, D):
     assert (np.abs(out["free_values"].cpu().numpy() - want) / scale).max() <= 1e-8
 
 
-@pytest.mark.parametrize("K", [2, 4, 6, 8, 10])
+@pytest.mark.parametrize("K", [2, 4, 5, 6, 7, 8, 9, 10, 11, 12])
 @pytest.mark.parametrize("D", [1, 2, 3])
 def test_two_kernel_generations_agree(ms, oracle, torch_cuda, monkeypatch, K, D):
-    """The second-generation kernel (tensor-memory block storage, TMA copy-out: even K <= 10) against the
+    """The second-generation kernel (tensor-memory block storage, TMA copy-out: K = 2 and 4 <= K <= 12, odd K with
+    the bottom-up lane one block short) against the
     first-generation thread-pair kernel on the same inputs, with non-zero end derivatives, cost, status,
     free derivatives, a ragged batch, and times computed on the device."""
     torch = torch_cuda
@@ -695,7 +696,7 @@ def test_two_kernel_generations_agree(ms, oracle, torch_cuda, monkeypatch, K, D)
         assert coeff_rel_err(a["coeffs"][i].cpu().numpy(), ref["coeffs"]) <= COEFF_TOL
 
 
-@pytest.mark.parametrize("K,D", [(4, 2), (12, 1), (10, 3)])
+@pytest.mark.parametrize("K,D", [(4, 2), (12, 1), (10, 3), (9, 3), (5, 2)])
 def test_two_batches_per_warp(ms, oracle, torch_cuda, monkeypatch, K, D):
     """Above two waves of CTAs a warp of the second-generation kernel takes two batches (second input buffer,
     one allocation / table / drain per CTA): a ragged batch just above that threshold against the first-generation

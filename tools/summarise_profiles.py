@@ -10,7 +10,7 @@ import shutil
 import subprocess
 
 G, P = "gpurun_out/", "profiles/"
-KERNEL = "_ZN7minsnap2tm24solve_standard_tm_kernelILi3ELb0ELb0EEEvNS_4fast10FastParamsEii14CUtensorMap_sti"
+KERNEL = "_ZN7minsnap2tm24solve_standard_tm_kernelILi3ELb0ELb0ELb0EEEvNS_4fast10FastParamsEii14CUtensorMap_sti"
 
 for page, out in (("source", "final_tm_src.csv"), ("raw", "final_tm_raw.csv")):
     with open(G + out, "w") as fh:
