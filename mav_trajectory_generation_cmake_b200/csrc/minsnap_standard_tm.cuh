@@ -214,6 +214,10 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   //   rec_tab[side][45 + a]          = side ? 0 : A1inv[1+a][1+a]                        (c_k from new_k)
   //   rec_tab[side][49 + a]          = side ? (-1)^(a+1) A1inv[1+a][1+a] : 0             (c_k from old_k)
   __shared__ __align__(16) double rec_tab[2][kRecTab];
+  // packed lower triangle of the per-segment cost form (doubled off-diagonal entries, tools/gen_tables.py); read
+  // from shared memory the 45 entries pass through vector registers for an instruction each -- as constant-bank
+  // operands they filled the uniform registers of the recovery loop (57.4 -> 62.7 us with cost)
+  __shared__ __align__(16) double cost_tab[kCost ? 46 : 2];
   const int lane = threadIdx.x & 31;
   // through a shuffle the compiler knows the warp index is warp-uniform: addresses and batch bases derived from
   // it stay in uniform registers, and the TMA operands need no per-lane vote loop
@@ -271,6 +275,8 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
   static_assert(2 * kRecTab <= kWarpsPerCta * 32, "one table entry per thread");
   if (threadIdx.x < 2 * kRecTab)
     __pipeline_memcpy_async(&rec_tab[0][0] + threadIdx.x, minsnap_tables::kRecoveryRoles_N10 + threadIdx.x, 8);
+  if (kCost && threadIdx.x < 46)
+    __pipeline_memcpy_async(cost_tab + threadIdx.x, minsnap_tables::kCostFormGlobal_N10_d4 + threadIdx.x, 8);
   __pipeline_commit();
   if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&coeff_map)) : "memory");
   // tensor memory: one allocation per CTA (warp 0), every warp works in its own lane quarter.  The warps meet
@@ -720,26 +726,33 @@ solve_standard_tm_kernel(FastParams p, int tmem_cols, int resident_warps, const 
       }
       double qsum = 0.0;
       if (kCost) {
-        // u^T Hred1 u * T^-7: the per-segment quadratic form in scaled variables.  (The packed
-        // lower-triangle form of the first-generation kernel, 54 instead of 90 multiply-adds per dimension, was
-        // measured here too: its 45 extra table constants push uniform-register fills into this loop, 57.4 ->
-        // 62.7 us per 65,536 solves with cost.)
+        // u^T Hred1 u * T^-7: the per-segment quadratic form in scaled variables over the packed lower
+        // triangle, every entry fetched once from shared memory and applied to the D dimensions.  The variables
+        // are in the lane's local orientation: time reversal leaves the form invariant when the position
+        // difference changes sign with the odd derivatives.
+        double fu0[D], qd[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          double qd = 0.0;
-#pragma unroll
-          for (int r = 0; r < 2 * kF + 1; ++r) {
-            const int hr = r == 0 ? 5 : (r <= kF ? r : r + 1);   // row of H1: dp -> 5, start k -> k, end k -> 5 + k
-            double row = 0.0;
-#pragma unroll
-            for (int s = 0; s < 2 * kF + 1; ++s) {
-              const int hs = s == 0 ? 5 : (s <= kF ? s : s + 1);
-              row = fma(H1T(hr, hs), (s == 0 ? flip[0] : 1.0) * u[s][d], row);
-            }
-            qd = fma(row, (r == 0 ? flip[0] : 1.0) * u[r][d], qd);
-          }
-          qsum += qd;
+          fu0[d] = flip[0] * u[0][d];
+          qd[d] = (cost_tab[0] * fu0[d]) * fu0[d];
         }
+#pragma unroll
+        for (int r = 1; r < 2 * kF + 1; ++r) {
+          double row[D];
+          const double c0 = cost_tab[tri(r, 0)], cr = cost_tab[tri(r, r)];
+#pragma unroll
+          for (int d = 0; d < D; ++d) row[d] = fma(c0, fu0[d], cr * u[r][d]);
+#pragma unroll
+          for (int s2 = 1; s2 < r; ++s2) {
+            const double c = cost_tab[tri(r, s2)];
+#pragma unroll
+            for (int d = 0; d < D; ++d) row[d] = fma(c, u[s2][d], row[d]);
+          }
+#pragma unroll
+          for (int d = 0; d < D; ++d) qd[d] = fma(row[d], u[r][d], qd[d]);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) qsum += qd[d];
       }
       if (kCost && jj >= 0) cost_acc = fma(qsum, i5 * i2, cost_acc);
       pending_j = j;   // this step's tile leaves during the next step (or after the loop)

@@ -171,6 +171,11 @@ def main():
                     for r in range(9):
                         fh.write("    " + ", ".join(lit(x) for x in t[r * (r + 1) // 2:(r + 1) * (r + 2) // 2]) + ",\n")
                     fh.write("};\n")
+                    # the same table in global memory, for kernels that stage it in shared memory by cp.async
+                    fh.write("MINSNAP_TABLE_GLOBAL_QUAL MINSNAP_TABLE_CONST double kCostFormGlobal_N10_d4[46] = {\n")
+                    for r in range(9):
+                        fh.write("    " + ", ".join(lit(x) for x in t[r * (r + 1) // 2:(r + 1) * (r + 2) // 2]) + ",\n")
+                    fh.write("    0.0,\n};\n")
             fh.write("\n")
         fh.write("}  // namespace minsnap_tables\n")
     print("wrote", os.path.normpath(OUT))
