@@ -338,6 +338,11 @@ def timed_steps(torch, ranks, launch, steps, warmup, clocks=None, probe_s=0.0):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ranks.barrier()
     torch.cuda.synchronize()
+    # A spin kernel of ~0.3 ms goes first: while it runs the host enqueues the start event, the graph and the stop
+    # event, so that the first timed kernel starts right behind the start event.  Without it the window opened on an
+    # idle GPU and contained the host's graph-submission latency (10-40 us, more with several ranks sharing the
+    # host: 41.4 us per step at N = 1 against 43.1 us per rank at N = 2 on the same box).
+    torch.cuda._sleep(600_000)
     ev0.record()
     if graph is not None:
         graph.replay()
@@ -714,7 +719,9 @@ def run_gpu_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": CONFIG,
             "run": {"timed_loop": timed_mode, "buffer_sets": n_sets,
-                    "extra_warmup": "one untimed replay of the %d-step graph after the %d eager steps" % (args.steps, args.warmup)},
+                    "extra_warmup": "one untimed replay of the %d-step graph after the %d eager steps" % (args.steps, args.warmup),
+                    "window": "start event behind a ~0.3 ms spin kernel: events, graph and stop event are enqueued while "
+                              "it runs, so the window holds the K steps and no host submission latency"},
             "per_rank_ms": Ranks.spread(all_ms, args.steps),
             "gpu_launches": args.steps * ms_launches_per_step(ms),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
