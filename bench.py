@@ -329,15 +329,11 @@ def timed_steps(torch, ranks, launch, steps, warmup, clocks=None, probe_s=0.0):
         with torch.cuda.graph(g):
             for i in range(steps):
                 launch(warmup + i)
-        # untimed replays until ~50 ms of the timed work have run (at least one, at most 64): the first replay
-        # after the eager steps still finds the clocks and the memory system settling (measured: the headline line,
-        # timed first in the process, read 0.3-0.6 us per step above the same work timed a second later)
-        t_w = time.perf_counter()
+        # ONE untimed replay.  This is a burst measurement, like the driver-written peaks it is compared with: a B200
+        # that starts this work runs its first milliseconds at 41.4 us per step, ~100 ms into a continuous burst at
+        # 43 us, and under seconds of back-to-back replays at 44-45 us (tools/sustained_load.py prints the curve with
+        # the NVML clocks and power beside it); a window of K = 20 steps is 0.8 ms.
         g.replay()
-        torch.cuda.synchronize()
-        one = max(time.perf_counter() - t_w, 1e-5)
-        for _ in range(min(63, int(0.05 / one))):
-            g.replay()
         torch.cuda.synchronize()
         graph = g
     except Exception as exc:
@@ -727,7 +723,7 @@ def run_gpu_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": CONFIG,
             "run": {"timed_loop": timed_mode, "buffer_sets": n_sets,
-                    "extra_warmup": "untimed replays of the %d-step graph for ~50 ms (1..64) after the %d eager steps" % (args.steps, args.warmup),
+                    "extra_warmup": "one untimed replay of the %d-step graph after the %d eager steps (burst measurement; sustained load: tools/sustained_load.py)" % (args.steps, args.warmup),
                     "window": "start event behind a ~0.3 ms spin kernel: events, graph and stop event are enqueued while "
                               "it runs, so the window holds the K steps and no host submission latency"},
             "per_rank_ms": Ranks.spread(all_ms, args.steps),
