@@ -329,12 +329,16 @@ def timed_steps(torch, ranks, launch, steps, warmup, clocks=None, probe_s=0.0):
         with torch.cuda.graph(g):
             for i in range(steps):
                 launch(warmup + i)
-        # ONE untimed replay.  This is a burst measurement, like the driver-written peaks it is compared with: a B200
-        # that starts this work runs its first milliseconds at 41.4 us per step, ~100 ms into a continuous burst at
-        # 43 us, and under seconds of back-to-back replays at 44-45 us (tools/sustained_load.py prints the curve with
-        # the NVML clocks and power beside it); a window of K = 20 steps is 0.8 ms.
+        # Untimed replays for ~8 ms (at least one).  This is a burst measurement, like the driver-written peaks it is
+        # compared with, taken on a GPU that is awake: after an idle second the first replay can still read 42.3 us per
+        # step, 5-50 ms of work later a step takes 41.3-41.5 us every time, from ~100 ms of continuous load on 42.4 us
+        # and under seconds of it 44 us at the 1 kW power cap (tools/warmup_curve.py, tools/sustained_load.py).
+        t_w = time.perf_counter()
         g.replay()
         torch.cuda.synchronize()
+        while time.perf_counter() - t_w < 0.008:
+            g.replay()
+            torch.cuda.synchronize()
         graph = g
     except Exception as exc:
         mode = "eager (graph capture failed: %s)" % type(exc).__name__
@@ -723,7 +727,7 @@ def run_gpu_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": CONFIG,
             "run": {"timed_loop": timed_mode, "buffer_sets": n_sets,
-                    "extra_warmup": "one untimed replay of the %d-step graph after the %d eager steps (burst measurement; sustained load: tools/sustained_load.py)" % (args.steps, args.warmup),
+                    "extra_warmup": "untimed replays of the %d-step graph for ~8 ms after the %d eager steps (burst measurement on an awake GPU: tools/warmup_curve.py; sustained load: tools/sustained_load.py)" % (args.steps, args.warmup),
                     "window": "start event behind a ~0.3 ms spin kernel: events, graph and stop event are enqueued while "
                               "it runs, so the window holds the K steps and no host submission latency"},
             "per_rank_ms": Ranks.spread(all_ms, args.steps),
