@@ -338,6 +338,11 @@ def timed_steps(torch, ranks, launch, steps, warmup, clocks=None, probe_s=0.0):
         torch.cuda.synchronize()
         while time.perf_counter() - t_w < 0.008:
             g.replay()
+            if clocks is not None:
+                # the first NVML clock / event-reason reads of a process take milliseconds and cost the kernels
+                # running beside them ~1 us per step (tools/nvml_perturbation.py); later reads do not: they are made
+                # here, under the same load, so that the read inside the timed window is not the first one
+                clocks.sample()
             torch.cuda.synchronize()
         graph = g
     except Exception as exc:
