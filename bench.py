@@ -97,7 +97,7 @@ class Clocks:
     NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.samples, self.reasons, self.timed_samples = [], set(), 0
+        self.samples, self.reasons, self.timed_samples, self.mem_mhz = [], set(), 0, None
         self.max_mhz, self.h, self.nv = None, None, None
         try:
             import pynvml as nv
@@ -129,12 +129,16 @@ class Clocks:
                     self.reasons.add(name)
             if timed:
                 self.timed_samples += 1
+                try:
+                    self.mem_mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM)
+                except Exception:
+                    pass
         except Exception as exc:
             self.reasons.add("nvml_error: %s" % type(exc).__name__)
 
     def summary(self):
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "mem_mhz_in_timed_region": self.mem_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples), "samples_inside_timed_region": self.timed_samples,
                 "how": "NVML from the main thread: inside the timed graph replay and every 10 ms during a load probe "
                        "(the same graph replayed for >= 0.2 s) right after it"}
@@ -604,6 +608,11 @@ def run_gpu_arm(args):
     pos_d, times_d, coeffs_d, step = solve_workload(ms, torch, pos_h, K_SEG, n_sets)
 
     clocks = Clocks(local)
+    # A rehearsal of the whole procedure, discarded: the FIRST timed window of a process read 42.2-42.4 us per step on
+    # every fresh box, whatever real warm-up preceded it, and the same work timed a moment later 41.1-41.5 us
+    # (profiles/r2_warmup_curve.txt, first trial; the other configurations below, timed later in the process, never
+    # showed it).
+    timed_steps(torch, ranks, step, args.steps, args.warmup)
     all_ms, timed_mode = timed_steps(torch, ranks, step, args.steps, args.warmup, clocks=clocks, probe_s=0.25)
     elapsed_ms = max(all_ms)
     ms_per_step = elapsed_ms / args.steps
@@ -732,7 +741,7 @@ def run_gpu_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": CONFIG,
             "run": {"timed_loop": timed_mode, "buffer_sets": n_sets,
-                    "extra_warmup": "untimed replays of the %d-step graph for ~8 ms after the %d eager steps (burst measurement on an awake GPU: tools/warmup_curve.py; sustained load: tools/sustained_load.py)" % (args.steps, args.warmup),
+                    "extra_warmup": "a discarded rehearsal of the whole timed procedure (the first timed window of a process reads ~1 us per step high), then the %d eager steps and untimed replays of the %d-step graph for ~8 ms (burst measurement on an awake GPU: tools/warmup_curve.py; sustained load: tools/sustained_load.py)" % (args.warmup, args.steps),
                     "window": "start event behind a ~0.3 ms spin kernel: events, graph and stop event are enqueued while "
                               "it runs, so the window holds the K steps and no host submission latency"},
             "per_rank_ms": Ranks.spread(all_ms, args.steps),
