@@ -256,6 +256,9 @@ struct SepLayout {
   static constexpr int kMid = 10 + kF * D;
 };
 
+// grid.y = part of the record a thread assembles (0: M, 1: h, 2: the coupling to the next separator and the couplings
+// of the trajectory ends): the kernel is a gather of ~100 values per separator with next to no arithmetic, and one
+// thread per (separator, part) keeps three times as many loads in flight as one thread per separator did.
 template <int D>
 __global__ void __launch_bounds__(128) assemble_separators_kernel(long B, int K, int m, const double* __restrict__ positions,
                                                                   const double* __restrict__ times,
@@ -268,52 +271,64 @@ __global__ void __launch_bounds__(128) assemble_separators_kernel(long B, int K,
   const int J = K / m, ns = J - 1, mA = ns / 2;
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * ns) return;
+  const int part = blockIdx.y;
   const long b = t % B;
   const int j = 1 + (int)(t / B);
   auto field = [&](int f, int chunk) { return __ldg(rec + ((long)f * J + chunk) * B + b); };
-  double M[10], h[kF][D];
-  {
+  const bool is_middle = j == mA + 1;
+  const int side = j > mA + 1;
+  const int i = side ? J - j : j;   // local index 1 .. mA
+  double* out = blocks + ((long)(i - 1) * L::kBlock * 2 + side) * B + b;   // entry e at out[e 2 B]
+  if (part < 2) {
     const int s = j * m;
     const double* tim = times + b * K;
     const double* pos = positions + b * (long)(K + 1) * D;
     TimePowers ta, tb;
     ta.set(__ldg(tim + s - 1));
     tb.set(__ldg(tim + s));
-    double da[D], db[D];
+    if (part == 0) {
+      double M[10];
+      fast::diag_block(ta, tb, M);
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const double p0 = __ldg(pos + s * D + d);
-      da[d] = p0 - __ldg(pos + (s - 1) * D + d);
-      db[d] = __ldg(pos + (s + 1) * D + d) - p0;
+      for (int e = 0; e < 10; ++e) M[e] = (M[e] - field(F::kRR + e, j - 1)) - field(F::kLL + e, j);
+      if (is_middle) {
+#pragma unroll
+        for (int e = 0; e < 10; ++e) middle[(long)e * B + b] = M[e];
+      } else {
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int q = 0; q <= a; ++q) out[(long)tri(a, q) * 2 * B] = (side && ((a + q) & 1)) ? -M[tri(a, q)] : M[tri(a, q)];
+      }
+    } else {
+      double da[D], db[D], h[kF][D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double p0 = __ldg(pos + s * D + d);
+        da[d] = p0 - __ldg(pos + (s - 1) * D + d);
+        db[d] = __ldg(pos + (s + 1) * D + d) - p0;
+      }
+      rhs_block<D>(ta, tb, da, db, h);
+#pragma unroll
+      for (int a = 0; a < kF; ++a)
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+          h[a][d] = (h[a][d] - field(F::kRr + a * D + d, j - 1)) - field(F::kRl + a * D + d, j);
+      if (is_middle) {
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) middle[(long)(10 + a * D + d) * B + b] = h[a][d];
+      } else {
+#pragma unroll
+        for (int a = 0; a < kF; ++a)
+#pragma unroll
+          for (int d = 0; d < D; ++d) out[(long)(10 + a * D + d) * 2 * B] = (side && !(a & 1)) ? -h[a][d] : h[a][d];
+      }
     }
-    fast::diag_block(ta, tb, M);
-    rhs_block<D>(ta, tb, da, db, h);
-#pragma unroll
-    for (int e = 0; e < 10; ++e) M[e] = (M[e] - field(F::kRR + e, j - 1)) - field(F::kLL + e, j);
-#pragma unroll
-    for (int a = 0; a < kF; ++a)
-#pragma unroll
-      for (int d = 0; d < D; ++d)
-        h[a][d] = (h[a][d] - field(F::kRr + a * D + d, j - 1)) - field(F::kRl + a * D + d, j);
+    return;
   }
-  if (j == mA + 1) {
-#pragma unroll
-    for (int e = 0; e < 10; ++e) middle[(long)e * B + b] = M[e];
-#pragma unroll
-    for (int a = 0; a < kF; ++a)
-#pragma unroll
-      for (int d = 0; d < D; ++d) middle[(long)(10 + a * D + d) * B + b] = h[a][d];
-  } else {
-    const int side = j > mA + 1;
-    const int i = side ? J - j : j;   // local index 1 .. mA
-    double* out = blocks + ((long)(i - 1) * L::kBlock * 2 + side) * B + b;   // entry e at out[e 2 B]
-#pragma unroll
-    for (int a = 0; a < kF; ++a) {
-#pragma unroll
-      for (int q = 0; q <= a; ++q) out[(long)tri(a, q) * 2 * B] = (side && ((a + q) & 1)) ? -M[tri(a, q)] : M[tri(a, q)];
-#pragma unroll
-      for (int d = 0; d < D; ++d) out[(long)(10 + a * D + d) * 2 * B] = (side && !(a & 1)) ? -h[a][d] : h[a][d];
-    }
+  if (!is_middle) {
     // coupling to the next local separator: top-down K_j^T (chunk j), bottom-up flip K_{j-1} flip (chunk j-1)
     const int chunk = side ? j - 1 : j;
 #pragma unroll
@@ -679,7 +694,7 @@ inline cudaError_t run_range(const FastParams& p, const RangeScratch<D>& w, cuda
   }
   {
     const int ns = J - 1;
-    assemble_separators_kernel<D><<<(unsigned)((p.B * ns + 127) / 128), 128, 0, s>>>(p.B, K, m, p.positions, p.times, w.rec,
+    assemble_separators_kernel<D><<<dim3((unsigned)((p.B * ns + 127) / 128), 3), 128, 0, s>>>(p.B, K, m, p.positions, p.times, w.rec,
                                                                                      w.sep_blocks, w.sep_edge, w.sep_middle);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     separator_solve_kernel<D><<<(unsigned)((p.B + 15) / 16), 32, 0, s>>>(p.B, K, m, p.end_derivatives, w.sep_blocks, w.sep_edge,
