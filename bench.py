@@ -368,7 +368,13 @@ def timed_steps(torch, ranks, launch, steps, warmup, clocks=None, probe_s=0.0):
             launch(warmup + i)
     ev1.record()
     if clocks is not None:
+        # the read is made once the start event has fired (the host polls it through the spin kernel) and counts
+        # as inside the window only if the stop event has not fired when it returns
+        while not ev0.query():
+            pass
         clocks.sample(timed=True)
+        if ev1.query():
+            clocks.timed_samples -= 1
     torch.cuda.synchronize()
     elapsed = ev0.elapsed_time(ev1)
     ranks.barrier()
